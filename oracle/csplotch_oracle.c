@@ -1,0 +1,1062 @@
+/*
+ * csplotch_oracle.c — TEST INFRASTRUCTURE ONLY (see csplotch_oracle.h).
+ *
+ * PARITY UNPINNED at the Stan boundary: no CmdStan in this image and the
+ * reference holds no golden vectors for this path.
+ *
+ * Every function cites the reference lines (relative to /root/reference) or
+ * the upstream Stan source file it restates.  Scalar, single-threaded per
+ * gene-chain (like one CmdStan process per chain); OpenMP only across
+ * gene-chains in the *_batch entry points.
+ */
+#include "csplotch_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------ */
+/* Stan Math scalar helpers                            */
+/* ------------------------------------------------------------------ */
+static double log1m(double x) { return log1p(-x); }
+static double log1p_exp(double x) { return x > 0 ? x + log1p(exp(-x)) : log1p(exp(x)); }
+static double log_sum_exp2(double a, double b) {
+  if (a == -INFINITY) return b;
+  if (a == INFINITY && b == INFINITY) return INFINITY;
+  if (a > b) return a + log1p_exp(b - a);
+  return b + log1p_exp(a - b);
+}
+static double inv_logit(double u) {
+  if (u < 0) {
+    double e = exp(u);
+    return e / (1.0 + e);
+  }
+  return 1.0 / (1.0 + exp(-u));
+}
+static double log_inv_logit(double u) { return u < 0 ? u - log1p(exp(u)) : -log1p(exp(-u)); }
+static double log1m_inv_logit(double u) { return u > 0 ? -u - log1p(exp(-u)) : -log1p(exp(u)); }
+
+/* ------------------------------------------------------------------ */
+/* Unconstrained layout: declaration order of the parameters{} block   */
+/* splotch_stan_model.stan:74-98, comp_splotch_stan_model.stan:81-108  */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int N, T, C, K, L1, L2, L3, L, zi, car, nb, fam;
+  int nbeta;
+  int o_psi, o_beta, o_tau, o_a, o_sigma, o_s2, o_s3, o_theta, o_phi, o_noise, D;
+} lay_t;
+
+static void layout(const orc_data *d, lay_t *l) {
+  int n = 0, t, o = 0;
+  for (t = 0; t < d->N_tissues; ++t) n += d->N_spots[t];
+  l->N = n;
+  l->T = d->N_tissues;
+  l->C = d->N_covariates;
+  l->fam = d->family;
+  l->K = (d->family == 1) ? d->N_celltypes : 1;
+  l->L1 = d->N_level_1;
+  l->L2 = d->N_level_2;
+  l->L3 = d->N_level_3;
+  l->L = l->L1 + l->L2 + l->L3;
+  l->zi = d->zi;
+  l->car = d->car;
+  l->nb = (d->family == 1) ? d->nb : 0;
+  l->nbeta = l->L * l->C * l->K;
+  l->o_psi = o;   o += l->car ? n : 0;
+  l->o_beta = o;  o += l->nbeta;
+  l->o_tau = o;   o += l->car ? 1 : 0;
+  l->o_a = o;     o += l->car ? 1 : 0;
+  l->o_sigma = o; o += 1;
+  l->o_s2 = o;    o += l->L2 ? 1 : 0;
+  l->o_s3 = o;    o += l->L3 ? 1 : 0;
+  l->o_theta = o; o += l->zi ? 1 : 0;
+  l->o_phi = o;   o += l->nb ? 1 : 0;
+  l->o_noise = o; o += n;
+  l->D = o;
+}
+
+/* position of beta_raw[i,j(,k)] inside the beta_raw block.
+ * matrix[L,C] (families 0,2): column-major i + L*j.
+ * row_vector[K] beta_raw[L,C] (family 1): stanc3 reads arrays outer-to-inner
+ * with the vector innermost: (i*C + j)*K + k. */
+static int bidx(const lay_t *l, int i, int j, int k) {
+  if (l->fam == 1) return (i * l->C + j) * l->K + k;
+  return i + l->L * j;
+}
+
+int32_t orc_num_spots(const orc_data *d) { lay_t l; layout(d, &l); return l.N; }
+int32_t orc_dim(const orc_data *d) { lay_t l; layout(d, &l); return l.D; }
+int32_t orc_num_outputs(const orc_data *d) {
+  lay_t l; layout(d, &l);
+  /* params (constrained, same count as D) + log_lambda + beta_level_1..3 */
+  return l.D + l.N + l.nbeta;
+}
+
+/* transformed parameters{}: beta_level_k, stacked as rows [0,L) of b[(i*C+j)*K+k].
+ * splotch_stan_model.stan:111-130, comp_splotch_stan_model.stan:124-150 */
+static void beta_levels(const orc_data *d, const lay_t *l, const double *braw, double s2, double s3,
+                        double *b) {
+  int i, j, k;
+  for (i = 0; i < l->L1; ++i)
+    for (j = 0; j < l->C; ++j)
+      for (k = 0; k < l->K; ++k) {
+        double r = braw[bidx(l, i, j, k)];
+        b[(i * l->C + j) * l->K + k] =
+            (l->fam == 1) ? r * d->beta_prior_std[k] + d->beta_prior_mean[k] : 2.0 * r;
+      }
+  for (i = 0; i < l->L2; ++i) {
+    int up = d->level_2_mapping[i] - 1;
+    for (j = 0; j < l->C; ++j)
+      for (k = 0; k < l->K; ++k)
+        b[((l->L1 + i) * l->C + j) * l->K + k] =
+            b[(up * l->C + j) * l->K + k] + s2 * braw[bidx(l, l->L1 + i, j, k)];
+  }
+  for (i = 0; i < l->L3; ++i) {
+    int up = l->L1 + d->level_3_mapping[i] - 1;
+    for (j = 0; j < l->C; ++j)
+      for (k = 0; k < l->K; ++k)
+        b[((l->L1 + l->L2 + i) * l->C + j) * l->K + k] =
+            b[(up * l->C + j) * l->K + k] + s3 * braw[bidx(l, l->L1 + l->L2 + i, j, k)];
+  }
+}
+
+/* first row of the deepest non-empty level (the one log_lambda indexes) */
+static int bottom_row0(const lay_t *l) {
+  if (l->L3) return l->L1 + l->L2;
+  if (l->L2) return l->L1;
+  return 0;
+}
+
+/* log_lambda: splotch_stan_model.stan:135-180, comp_splotch_stan_model.stan:155-206 */
+static void compute_log_lambda(const orc_data *d, const lay_t *l, const double *b, const double *psi,
+                               double sigma, const double *noise, double *ll, int *row_of_spot) {
+  int t, j = 0, s, k, r0 = bottom_row0(l);
+  for (t = 0; t < l->T; ++t) {
+    int row = r0 + d->tissue_mapping[t] - 1;
+    for (s = 0; s < d->N_spots[t]; ++s, ++j) {
+      const double *bj = b + (row * l->C + (d->D[j] - 1)) * l->K;
+      double v;
+      if (l->fam == 1) {
+        v = 0.0;
+        for (k = 0; k < l->K; ++k) v += bj[k] * d->E[(size_t)j * l->K + k];
+      } else {
+        v = bj[0];
+      }
+      if (l->car) v += psi[j];
+      v += 0.3 * sigma * noise[j];
+      ll[j] = v;
+      if (row_of_spot) row_of_spot[j] = row;
+    }
+  }
+}
+
+/* (W psi)_i in the summation order of each model family:
+ * families 0,1: edge-pair loop, splotch_stan_model.stan:11-14
+ * family 2: csr_matrix_times_vector, splotch_stan_model_csr.stan:22 */
+static void car_Wpsi(const orc_data *d, const lay_t *l, const double *psi, double *Wpsi) {
+  int i, e;
+  memset(Wpsi, 0, sizeof(double) * (size_t)l->N);
+  if (l->fam == 2) {
+    for (i = 0; i < l->N; ++i) {
+      double s = 0.0;
+      for (e = d->U[i] - 1; e < d->U[i + 1] - 1; ++e) s += 1.0 * psi[d->V[e] - 1];
+      Wpsi[i] = s;
+    }
+  } else {
+    for (e = 0; e < d->W_n; ++e) {
+      int i1 = d->W_sparse[2 * e] - 1, i2 = d->W_sparse[2 * e + 1] - 1;
+      Wpsi[i1] += psi[i2];
+      Wpsi[i2] += psi[i1];
+    }
+  }
+}
+
+double orc_log_prob_grad(const orc_data *d, const double *th, double *grad, int32_t jacobian) {
+  lay_t l;
+  int i, j, k, N;
+  double lp = 0.0;
+  double tau = 0, a = 0, sigma, s2 = 0, s3 = 0, theta = 0;
+  double d_tau = 0, d_a = 0, d_sigma = 0, d_s2 = 0, d_s3 = 0, d_theta = 0;
+  const double *psi, *braw, *noise;
+  double *b, *adj_b, *ll, *adj_ll, *Wpsi = NULL;
+  int *row_of_spot;
+
+  layout(d, &l);
+  N = l.N;
+  if (l.nb) return NAN; /* NB/ZINB branch (comp_…stan:248-265) is SURVEY §8 f3 "next" */
+  psi = th + l.o_psi;
+  braw = th + l.o_beta;
+  noise = th + l.o_noise;
+
+  /* ---- parameters{}: constraining transforms + log-Jacobians (A.1/A.2) ---- */
+  if (l.car) {
+    double u = th[l.o_tau];
+    tau = exp(u);
+    if (jacobian) lp += u;
+    u = th[l.o_a];
+    a = inv_logit(u);
+    if (jacobian) lp += log_inv_logit(u) + log1m_inv_logit(u);
+  }
+  sigma = exp(th[l.o_sigma]);
+  if (jacobian) lp += th[l.o_sigma];
+  if (l.L2) { s2 = exp(th[l.o_s2]); if (jacobian) lp += th[l.o_s2]; }
+  if (l.L3) { s3 = exp(th[l.o_s3]); if (jacobian) lp += th[l.o_s3]; }
+  if (l.zi) {
+    double u = th[l.o_theta];
+    theta = inv_logit(u);
+    if (jacobian) lp += log_inv_logit(u) + log1m_inv_logit(u);
+  }
+
+  /* ---- transformed parameters{} ---- */
+  b = (double *)malloc(sizeof(double) * (size_t)(l.nbeta > 0 ? l.nbeta : 1));
+  adj_b = (double *)calloc((size_t)(l.nbeta > 0 ? l.nbeta : 1), sizeof(double));
+  ll = (double *)malloc(sizeof(double) * (size_t)N);
+  adj_ll = (double *)calloc((size_t)N, sizeof(double));
+  row_of_spot = (int *)malloc(sizeof(int) * (size_t)N);
+  beta_levels(d, &l, braw, s2, s3, b);
+  compute_log_lambda(d, &l, b, psi, sigma, noise, ll, row_of_spot);
+
+  /* ---- model{} ---- */
+  if (l.car) {
+    double quadD = 0.0, quadW = 0.0, ldet = 0.0, dldet = 0.0, Q;
+    /* tau ~ inv_gamma(1,1): -(alpha+1) log tau - beta/tau */
+    lp += -2.0 * log(tau) - 1.0 / tau;
+    d_tau += -2.0 / tau + 1.0 / (tau * tau);
+    /* psi ~ sparse_car(...)  splotch_stan_model.stan:4-17 / _csr.stan:4-25 */
+    Wpsi = (double *)malloc(sizeof(double) * (size_t)N);
+    car_Wpsi(d, &l, psi, Wpsi);
+    for (i = 0; i < N; ++i) {
+      quadD += (psi[i] * d->D_sparse[i]) * psi[i];
+      quadW += Wpsi[i] * psi[i];
+      ldet += log1m(a * d->eig_values[i]);
+      dldet += -d->eig_values[i] / (1.0 - a * d->eig_values[i]);
+    }
+    Q = quadD - a * quadW;
+    lp += 0.5 * (N * log(tau) + ldet - tau * Q);
+    d_tau += 0.5 * (N / tau - Q);
+    d_a += 0.5 * (dldet + tau * quadW);
+  }
+  if (l.zi) {
+    /* theta ~ beta(1,2) */
+    lp += log1m(theta);
+    d_theta += -1.0 / (1.0 - theta);
+  }
+  /* sigma ~ normal(0,1); noise_raw ~ normal(0,1) */
+  lp += -0.5 * sigma * sigma;
+  d_sigma += -sigma;
+  {
+    double ss = 0.0;
+    for (j = 0; j < N; ++j) ss += noise[j] * noise[j];
+    lp += -0.5 * ss;
+  }
+  if (l.L2) { lp += -0.5 * s2 * s2; d_s2 += -s2; }
+  if (l.L3) { lp += -0.5 * s3 * s3; d_s3 += -s3; }
+  {
+    double ss = 0.0;
+    for (i = 0; i < l.nbeta; ++i) ss += braw[i] * braw[i];
+    lp += -0.5 * ss;
+  }
+
+  /* likelihood */
+  if (l.zi) {
+    double heads = log(theta), tails = log1m(theta);
+    if (l.fam == 2) {
+      /* zero / non-zero split: splotch_stan_model_csr.stan:254-268 */
+      int n_nonzero = 0;
+      double acc = 0.0;
+      for (j = 0; j < N; ++j) {
+        if (d->counts[j] == 0) {
+          double eta = ll[j] + log(d->size_factors[j]);
+          double mu = exp(eta);
+          double B = tails + (-mu);
+          double lse = log_sum_exp2(heads, B);
+          double wA = exp(heads - lse), wB = exp(B - lse);
+          lp += lse;
+          adj_ll[j] += wB * (-mu);
+          d_theta += wA / theta - wB / (1.0 - theta);
+        } else {
+          ++n_nonzero;
+        }
+      }
+      lp += n_nonzero * tails;
+      d_theta += -(double)n_nonzero / (1.0 - theta);
+      for (j = 0; j < N; ++j) {
+        int y = d->counts[j];
+        if (y != 0) {
+          double eta = ll[j] + log(d->size_factors[j]);
+          double mu = exp(eta);
+          acc += y * eta - mu - lgamma(y + 1.0);
+          adj_ll[j] += y - mu;
+        }
+      }
+      lp += acc;
+    } else {
+      /* per-spot loop: splotch_stan_model.stan:209-222, comp_…stan:267-280 */
+      for (j = 0; j < N; ++j) {
+        int y = d->counts[j];
+        double eta = ll[j] + log(d->size_factors[j]);
+        double mu = exp(eta);
+        if (y == 0) {
+          double B = tails + (-mu);
+          double lse = log_sum_exp2(heads, B);
+          double wA = exp(heads - lse), wB = exp(B - lse);
+          lp += lse;
+          adj_ll[j] += wB * (-mu);
+          d_theta += wA / theta - wB / (1.0 - theta);
+        } else {
+          lp += tails + (y * eta - mu - lgamma(y + 1.0));
+          adj_ll[j] += y - mu;
+          d_theta += -1.0 / (1.0 - theta);
+        }
+      }
+    }
+  } else {
+    /* counts ~ poisson_log(log_lambda + log_size_factors): lgamma(y+1) dropped */
+    double acc = 0.0;
+    for (j = 0; j < N; ++j) {
+      int y = d->counts[j];
+      double eta = ll[j] + log(d->size_factors[j]);
+      double mu = exp(eta);
+      acc += y * eta - mu;
+      adj_ll[j] += y - mu;
+    }
+    lp += acc;
+  }
+
+  if (grad) {
+    double sum_ng = 0.0;
+    memset(grad, 0, sizeof(double) * (size_t)l.D);
+    /* reverse of log_lambda assembly */
+    for (j = 0; j < N; ++j) {
+      double gj = adj_ll[j];
+      double *abj = adj_b + (row_of_spot[j] * l.C + (d->D[j] - 1)) * l.K;
+      if (l.fam == 1)
+        for (k = 0; k < l.K; ++k) abj[k] += gj * d->E[(size_t)j * l.K + k];
+      else
+        abj[0] += gj;
+      if (l.car) grad[l.o_psi + j] += gj;
+      grad[l.o_noise + j] += 0.3 * sigma * gj - noise[j];
+      sum_ng += noise[j] * gj;
+    }
+    d_sigma += 0.3 * sum_ng;
+    if (l.car)
+      for (i = 0; i < N; ++i) grad[l.o_psi + i] += -tau * (d->D_sparse[i] * psi[i] - a * Wpsi[i]);
+    /* reverse of the hierarchy (A.3), deepest level first */
+    for (i = l.L3 - 1; i >= 0; --i) {
+      int row = l.L1 + l.L2 + i, up = l.L1 + d->level_3_mapping[i] - 1;
+      for (j = 0; j < l.C; ++j)
+        for (k = 0; k < l.K; ++k) {
+          double ab = adj_b[(row * l.C + j) * l.K + k];
+          double r = braw[bidx(&l, row, j, k)];
+          grad[l.o_beta + bidx(&l, row, j, k)] += s3 * ab;
+          d_s3 += ab * r;
+          adj_b[(up * l.C + j) * l.K + k] += ab;
+        }
+    }
+    for (i = l.L2 - 1; i >= 0; --i) {
+      int row = l.L1 + i, up = d->level_2_mapping[i] - 1;
+      for (j = 0; j < l.C; ++j)
+        for (k = 0; k < l.K; ++k) {
+          double ab = adj_b[(row * l.C + j) * l.K + k];
+          double r = braw[bidx(&l, row, j, k)];
+          grad[l.o_beta + bidx(&l, row, j, k)] += s2 * ab;
+          d_s2 += ab * r;
+          adj_b[(up * l.C + j) * l.K + k] += ab;
+        }
+    }
+    for (i = 0; i < l.L1; ++i)
+      for (j = 0; j < l.C; ++j)
+        for (k = 0; k < l.K; ++k) {
+          double ab = adj_b[(i * l.C + j) * l.K + k];
+          grad[l.o_beta + bidx(&l, i, j, k)] += (l.fam == 1 ? d->beta_prior_std[k] : 2.0) * ab;
+        }
+    for (i = 0; i < l.nbeta; ++i) grad[l.o_beta + i] += -braw[i];
+    /* chain to the unconstrained scale */
+    if (l.car) {
+      grad[l.o_tau] = tau * d_tau + (jacobian ? 1.0 : 0.0);
+      grad[l.o_a] = a * (1.0 - a) * d_a + (jacobian ? (1.0 - 2.0 * a) : 0.0);
+    }
+    grad[l.o_sigma] = sigma * d_sigma + (jacobian ? 1.0 : 0.0);
+    if (l.L2) grad[l.o_s2] = s2 * d_s2 + (jacobian ? 1.0 : 0.0);
+    if (l.L3) grad[l.o_s3] = s3 * d_s3 + (jacobian ? 1.0 : 0.0);
+    if (l.zi) grad[l.o_theta] = theta * (1.0 - theta) * d_theta + (jacobian ? (1.0 - 2.0 * theta) : 0.0);
+  }
+
+  free(b); free(adj_b); free(ll); free(adj_ll); free(row_of_spot);
+  if (Wpsi) free(Wpsi);
+  return lp;
+}
+
+/* write_array: constrained parameters in declaration order, then transformed
+ * parameters log_lambda, beta_level_1..3 — every container column-major
+ * (Stan CSV order). */
+void orc_write_array(const orc_data *d, const double *th, double *out) {
+  lay_t l;
+  int i, j, k, o = 0, lev;
+  double sigma, s2 = 0, s3 = 0;
+  double *b, *ll;
+  layout(d, &l);
+  sigma = exp(th[l.o_sigma]);
+  if (l.L2) s2 = exp(th[l.o_s2]);
+  if (l.L3) s3 = exp(th[l.o_s3]);
+  if (l.car) for (i = 0; i < l.N; ++i) out[o++] = th[l.o_psi + i];
+  /* beta_raw column-major over (i,j[,k]): first index fastest */
+  for (k = 0; k < l.K; ++k)
+    for (j = 0; j < l.C; ++j)
+      for (i = 0; i < l.L; ++i) out[o++] = th[l.o_beta + bidx(&l, i, j, k)];
+  if (l.car) { out[o++] = exp(th[l.o_tau]); out[o++] = inv_logit(th[l.o_a]); }
+  out[o++] = sigma;
+  if (l.L2) out[o++] = s2;
+  if (l.L3) out[o++] = s3;
+  if (l.zi) out[o++] = inv_logit(th[l.o_theta]);
+  if (l.nb) out[o++] = 1e-6 + exp(th[l.o_phi]);
+  for (i = 0; i < l.N; ++i) out[o++] = th[l.o_noise + i];
+  b = (double *)malloc(sizeof(double) * (size_t)(l.nbeta > 0 ? l.nbeta : 1));
+  ll = (double *)malloc(sizeof(double) * (size_t)l.N);
+  beta_levels(d, &l, th + l.o_beta, s2, s3, b);
+  compute_log_lambda(d, &l, b, th + l.o_psi, sigma, th + l.o_noise, ll, NULL);
+  for (i = 0; i < l.N; ++i) out[o++] = ll[i];
+  for (lev = 0; lev < 3; ++lev) {
+    int r0 = lev == 0 ? 0 : (lev == 1 ? l.L1 : l.L1 + l.L2);
+    int nr = lev == 0 ? l.L1 : (lev == 1 ? l.L2 : l.L3);
+    for (k = 0; k < l.K; ++k)
+      for (j = 0; j < l.C; ++j)
+        for (i = 0; i < nr; ++i) out[o++] = b[((r0 + i) * l.C + j) * l.K + k];
+  }
+  free(b); free(ll);
+}
+
+void orc_unconstrain(const orc_data *d, const double *par, double *th) {
+  lay_t l;
+  int i, j, k, o = 0;
+  layout(d, &l);
+  if (l.car) for (i = 0; i < l.N; ++i) th[l.o_psi + i] = par[o++];
+  for (k = 0; k < l.K; ++k)
+    for (j = 0; j < l.C; ++j)
+      for (i = 0; i < l.L; ++i) th[l.o_beta + bidx(&l, i, j, k)] = par[o++];
+  if (l.car) {
+    double a;
+    th[l.o_tau] = log(par[o++]);
+    a = par[o++];
+    th[l.o_a] = log(a) - log1p(-a);
+  }
+  th[l.o_sigma] = log(par[o++]);
+  if (l.L2) th[l.o_s2] = log(par[o++]);
+  if (l.L3) th[l.o_s3] = log(par[o++]);
+  if (l.zi) { double t = par[o++]; th[l.o_theta] = log(t) - log1p(-t); }
+  if (l.nb) th[l.o_phi] = log(par[o++] - 1e-6);
+  for (i = 0; i < l.N; ++i) th[l.o_noise + i] = par[o++];
+}
+
+/* ------------------------------------------------------------------ */
+/* Philox4x32-10 and the keyed stream                  */
+/* ------------------------------------------------------------------ */
+void orc_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                uint32_t out[4]) {
+  int r;
+  for (r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+enum { PURP_INIT = 1, PURP_MOMENTUM = 2, PURP_SS_MOMENTUM = 3, PURP_DIRECTION = 4,
+       PURP_ACCEPT = 5, PURP_RESERVOIR = 6 };
+
+/* 53-bit uniform in the open interval (0,1) */
+static double u53(uint32_t hi, uint32_t lo) {
+  uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
+  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+typedef struct { uint32_t seed, chain, gene; } rng_t;
+
+/* two uniforms: key=(seed,chain), counter=(index, iteration, purpose<<24|sub, gene) */
+static void rng_u2(const rng_t *r, int purpose, uint32_t sub, uint32_t iter, uint32_t idx, double *u0,
+                   double *u1) {
+  uint32_t o[4];
+  orc_philox(r->seed, r->chain, idx, iter, ((uint32_t)purpose << 24) | (sub & 0xFFFFFFu), r->gene, o);
+  *u0 = u53(o[0], o[1]);
+  *u1 = u53(o[2], o[3]);
+}
+static double rng_u(const rng_t *r, int purpose, uint32_t sub, uint32_t iter, uint32_t idx) {
+  double a, b;
+  rng_u2(r, purpose, sub, iter, idx, &a, &b);
+  return a;
+}
+/* standard normals for elements (2*pair, 2*pair+1): Box–Muller */
+static void rng_n2(const rng_t *r, int purpose, uint32_t sub, uint32_t iter, uint32_t pair, double *n0,
+                   double *n1) {
+  double u0, u1, rad, ang;
+  rng_u2(r, purpose, sub, iter, pair, &u0, &u1);
+  rad = sqrt(-2.0 * log(u0));
+  ang = 6.283185307179586476925286766559 * u1;
+  *n0 = rad * cos(ang);
+  *n1 = rad * sin(ang);
+}
+
+/* ------------------------------------------------------------------ */
+/* Hamiltonian, integrator (stan/mcmc/hmc: diag_e_metric.hpp,          */
+/* expl_leapfrog.hpp, ps_point.hpp)                                    */
+/* ------------------------------------------------------------------ */
+typedef struct { double *q, *p, *g; double V; } ps_t;
+
+typedef struct {
+  int D;
+  orc_density_fn fn;
+  void *ctx;
+  double *inv_metric;
+  double eps;
+  int max_depth;
+  double max_deltaH;
+  rng_t rng;
+  int64_t n_grad;
+  double *tmp;
+  ps_t z;
+} hmc_t;
+
+static void ps_alloc(ps_t *z, int D) {
+  z->q = (double *)calloc((size_t)D, sizeof(double));
+  z->p = (double *)calloc((size_t)D, sizeof(double));
+  z->g = (double *)calloc((size_t)D, sizeof(double));
+  z->V = 0;
+}
+static void ps_free(ps_t *z) { free(z->q); free(z->p); free(z->g); }
+static void ps_copy(ps_t *dst, const ps_t *src, int D) {
+  memcpy(dst->q, src->q, sizeof(double) * (size_t)D);
+  memcpy(dst->p, src->p, sizeof(double) * (size_t)D);
+  memcpy(dst->g, src->g, sizeof(double) * (size_t)D);
+  dst->V = src->V;
+}
+
+/* hamiltonian.update_potential_gradient: V = -lp, g = -grad lp */
+static void update_pg(hmc_t *s, ps_t *z) {
+  int i;
+  double lp = s->fn(s->ctx, z->q, s->tmp);
+  s->n_grad++;
+  z->V = -lp;
+  for (i = 0; i < s->D; ++i) z->g[i] = -s->tmp[i];
+}
+static double kinetic(const hmc_t *s, const ps_t *z) {
+  int i;
+  double t = 0.0;
+  for (i = 0; i < s->D; ++i) t += s->inv_metric[i] * z->p[i] * z->p[i];
+  return 0.5 * t;
+}
+static double hamil(const hmc_t *s, const ps_t *z) { return kinetic(s, z) + z->V; }
+
+/* expl_leapfrog::evolve */
+static void leapfrog(hmc_t *s, ps_t *z, double eps) {
+  int i;
+  for (i = 0; i < s->D; ++i) z->p[i] -= 0.5 * eps * z->g[i];
+  for (i = 0; i < s->D; ++i) z->q[i] += eps * s->inv_metric[i] * z->p[i];
+  update_pg(s, z);
+  for (i = 0; i < s->D; ++i) z->p[i] -= 0.5 * eps * z->g[i];
+}
+
+/* diag_e_metric::sample_p: p_i = N(0,1)/sqrt(inv_metric_i) */
+static void sample_p(hmc_t *s, ps_t *z, int purpose, uint32_t sub, uint32_t iter) {
+  int pr;
+  for (pr = 0; 2 * pr < s->D; ++pr) {
+    double n0, n1;
+    rng_n2(&s->rng, purpose, sub, iter, (uint32_t)pr, &n0, &n1);
+    z->p[2 * pr] = n0 / sqrt(s->inv_metric[2 * pr]);
+    if (2 * pr + 1 < s->D) z->p[2 * pr + 1] = n1 / sqrt(s->inv_metric[2 * pr + 1]);
+  }
+}
+
+void orc_leapfrog_fixed(const orc_data *d, const double *theta0, const double *p0,
+                        const double *inv_metric, double eps, int32_t n_steps, double *theta_out,
+                        double *p_out, double *H_out, double *traj);
+
+/* ------------------------------------------------------------------ */
+/* NUTS transition (stan/mcmc/hmc/nuts/base_nuts.hpp)                  */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int n_leapfrog;
+  int divergent;
+  double sum_metro_prob;
+  double lsw_run;  /* running log-sum-weight of the subtree being built (leaf order) */
+  double *q_prop;  /* reservoir candidate inside the new subtree */
+  double V_prop, h_prop;
+  uint32_t iter;
+  double H0;
+} tree_t;
+
+static int crit(const double *ps_a, const double *ps_b, const double *rho, int D) {
+  int i;
+  double da = 0.0, db = 0.0;
+  for (i = 0; i < D; ++i) { da += ps_a[i] * rho[i]; db += ps_b[i] * rho[i]; }
+  return db > 0 && da > 0;
+}
+
+/* base_nuts::build_tree.  Deviation from upstream, distribution-preserving:
+ * the uniform-within-subtree proposal (upstream: pairwise tournament with
+ * probability w_right/w_subtree at every internal node) is drawn by weighted
+ * reservoir sampling in leaf order, P(leaf) = w_leaf / w_subtree in both.  The
+ * product uses the same rule so that draws are comparable one to one. */
+static int build_tree(hmc_t *s, int depth, double *p_sharp_beg, double *p_sharp_end, double *rho,
+                      double *p_beg, double *p_end, double sign, tree_t *tr) {
+  int D = s->D, i, valid_init, valid_final, persist;
+  double *p_init_end, *p_sharp_init_end, *rho_init, *p_final_beg, *p_sharp_final_beg, *rho_final, *rho_ext;
+  if (depth == 0) {
+    double h, w, u;
+    leapfrog(s, &s->z, sign * s->eps);
+    tr->n_leapfrog++;
+    h = hamil(s, &s->z);
+    if (isnan(h)) h = INFINITY;
+    if ((h - tr->H0) > s->max_deltaH) tr->divergent = 1;
+    w = tr->H0 - h;
+    tr->lsw_run = log_sum_exp2(tr->lsw_run, w);
+    tr->sum_metro_prob += (w > 0) ? 1.0 : exp(w);
+    u = rng_u(&s->rng, PURP_RESERVOIR, 0, tr->iter, (uint32_t)tr->n_leapfrog);
+    if (!tr->divergent && u < exp(w - tr->lsw_run)) {
+      memcpy(tr->q_prop, s->z.q, sizeof(double) * (size_t)D);
+      tr->V_prop = s->z.V;
+      tr->h_prop = h;
+    }
+    for (i = 0; i < D; ++i) {
+      p_sharp_beg[i] = s->inv_metric[i] * s->z.p[i];
+      p_sharp_end[i] = p_sharp_beg[i];
+      rho[i] += s->z.p[i];
+      p_beg[i] = s->z.p[i];
+      p_end[i] = s->z.p[i];
+    }
+    return !tr->divergent;
+  }
+  p_init_end = (double *)calloc((size_t)D * 7, sizeof(double));
+  p_sharp_init_end = p_init_end + D;
+  rho_init = p_init_end + 2 * D;
+  p_final_beg = p_init_end + 3 * D;
+  p_sharp_final_beg = p_init_end + 4 * D;
+  rho_final = p_init_end + 5 * D;
+  rho_ext = p_init_end + 6 * D;
+
+  valid_init = build_tree(s, depth - 1, p_sharp_beg, p_sharp_init_end, rho_init, p_beg, p_init_end, sign, tr);
+  if (!valid_init) { free(p_init_end); return 0; }
+  valid_final = build_tree(s, depth - 1, p_sharp_final_beg, p_sharp_end, rho_final, p_final_beg, p_end, sign, tr);
+  if (!valid_final) { free(p_init_end); return 0; }
+
+  for (i = 0; i < D; ++i) rho_ext[i] = rho_init[i] + rho_final[i]; /* rho_subtree */
+  for (i = 0; i < D; ++i) rho[i] += rho_ext[i];
+  persist = crit(p_sharp_beg, p_sharp_end, rho_ext, D);
+  for (i = 0; i < D; ++i) rho_ext[i] = rho_init[i] + p_final_beg[i];
+  persist &= crit(p_sharp_beg, p_sharp_final_beg, rho_ext, D);
+  for (i = 0; i < D; ++i) rho_ext[i] = rho_final[i] + p_init_end[i];
+  persist &= crit(p_sharp_init_end, p_sharp_end, rho_ext, D);
+  free(p_init_end);
+  return persist;
+}
+
+typedef struct {
+  double lp, accept_stat, stepsize, energy;
+  int treedepth, n_leapfrog, divergent;
+} draw_info_t;
+
+/* base_nuts::transition; q_cur in/out */
+static void nuts_transition(hmc_t *s, double *q_cur, uint32_t iter, draw_info_t *info) {
+  int D = s->D, i, depth = 0;
+  ps_t z_fwd, z_bck;
+  double *buf = (double *)calloc((size_t)D * 13, sizeof(double));
+  double *p_sharp_fwd_fwd = buf, *p_sharp_fwd_bck = buf + D, *p_sharp_bck_fwd = buf + 2 * D,
+         *p_sharp_bck_bck = buf + 3 * D, *p_fwd_fwd = buf + 4 * D, *p_fwd_bck = buf + 5 * D,
+         *p_bck_fwd = buf + 6 * D, *p_bck_bck = buf + 7 * D, *rho = buf + 8 * D, *rho_fwd = buf + 9 * D,
+         *rho_bck = buf + 10 * D, *rho_ext = buf + 11 * D, *q_sample = buf + 12 * D;
+  double *q_prop = (double *)calloc((size_t)D, sizeof(double));
+  double log_sum_weight = 0.0, V_sample, h_sample;
+  tree_t tr;
+
+  memcpy(s->z.q, q_cur, sizeof(double) * (size_t)D);
+  sample_p(s, &s->z, PURP_MOMENTUM, 0, iter);
+  update_pg(s, &s->z); /* hamiltonian.init */
+
+  ps_alloc(&z_fwd, D); ps_alloc(&z_bck, D);
+  ps_copy(&z_fwd, &s->z, D); ps_copy(&z_bck, &s->z, D);
+  memcpy(q_sample, s->z.q, sizeof(double) * (size_t)D);
+  V_sample = s->z.V;
+  for (i = 0; i < D; ++i) {
+    double ps = s->inv_metric[i] * s->z.p[i];
+    p_sharp_fwd_fwd[i] = p_sharp_fwd_bck[i] = p_sharp_bck_fwd[i] = p_sharp_bck_bck[i] = ps;
+    p_fwd_fwd[i] = p_fwd_bck[i] = p_bck_fwd[i] = p_bck_bck[i] = s->z.p[i];
+    rho[i] = s->z.p[i];
+  }
+  tr.H0 = hamil(s, &s->z);
+  h_sample = tr.H0;
+  tr.n_leapfrog = 0; tr.divergent = 0; tr.sum_metro_prob = 0.0; tr.iter = iter;
+  tr.q_prop = q_prop;
+
+  while (depth < s->max_depth) {
+    int valid_subtree, persist;
+    double log_sum_weight_subtree, u;
+    memset(rho_fwd, 0, sizeof(double) * (size_t)D);
+    memset(rho_bck, 0, sizeof(double) * (size_t)D);
+    tr.lsw_run = -INFINITY;
+    tr.V_prop = 0; tr.h_prop = 0;
+    u = rng_u(&s->rng, PURP_DIRECTION, 0, iter, (uint32_t)depth);
+    if (u > 0.5) {
+      ps_copy(&s->z, &z_fwd, D);
+      memcpy(rho_bck, rho, sizeof(double) * (size_t)D);
+      memcpy(p_bck_fwd, p_fwd_fwd, sizeof(double) * (size_t)D);
+      memcpy(p_sharp_bck_fwd, p_sharp_fwd_fwd, sizeof(double) * (size_t)D);
+      valid_subtree = build_tree(s, depth, p_sharp_fwd_bck, p_sharp_fwd_fwd, rho_fwd, p_fwd_bck, p_fwd_fwd, 1.0, &tr);
+      ps_copy(&z_fwd, &s->z, D);
+    } else {
+      ps_copy(&s->z, &z_bck, D);
+      memcpy(rho_fwd, rho, sizeof(double) * (size_t)D);
+      memcpy(p_fwd_bck, p_bck_bck, sizeof(double) * (size_t)D);
+      memcpy(p_sharp_fwd_bck, p_sharp_bck_bck, sizeof(double) * (size_t)D);
+      valid_subtree = build_tree(s, depth, p_sharp_bck_fwd, p_sharp_bck_bck, rho_bck, p_bck_fwd, p_bck_bck, -1.0, &tr);
+      ps_copy(&z_bck, &s->z, D);
+    }
+    if (!valid_subtree) break;
+    ++depth;
+    log_sum_weight_subtree = tr.lsw_run;
+    if (log_sum_weight_subtree > log_sum_weight) {
+      memcpy(q_sample, q_prop, sizeof(double) * (size_t)D);
+      V_sample = tr.V_prop; h_sample = tr.h_prop;
+    } else {
+      double accept_prob = exp(log_sum_weight_subtree - log_sum_weight);
+      double ua = rng_u(&s->rng, PURP_ACCEPT, 0, iter, (uint32_t)depth);
+      if (ua < accept_prob) {
+        memcpy(q_sample, q_prop, sizeof(double) * (size_t)D);
+        V_sample = tr.V_prop; h_sample = tr.h_prop;
+      }
+    }
+    log_sum_weight = log_sum_exp2(log_sum_weight, log_sum_weight_subtree);
+    for (i = 0; i < D; ++i) rho[i] = rho_bck[i] + rho_fwd[i];
+    persist = crit(p_sharp_bck_bck, p_sharp_fwd_fwd, rho, D);
+    for (i = 0; i < D; ++i) rho_ext[i] = rho_bck[i] + p_fwd_bck[i];
+    persist &= crit(p_sharp_bck_bck, p_sharp_fwd_bck, rho_ext, D);
+    for (i = 0; i < D; ++i) rho_ext[i] = rho_fwd[i] + p_bck_fwd[i];
+    persist &= crit(p_sharp_bck_fwd, p_sharp_fwd_fwd, rho_ext, D);
+    if (!persist) break;
+  }
+  info->n_leapfrog = tr.n_leapfrog;
+  info->treedepth = depth;
+  info->divergent = tr.divergent;
+  info->accept_stat = tr.sum_metro_prob / (double)tr.n_leapfrog;
+  info->lp = -V_sample;
+  info->energy = h_sample;
+  info->stepsize = s->eps;
+  memcpy(q_cur, q_sample, sizeof(double) * (size_t)D);
+  ps_free(&z_fwd); ps_free(&z_bck);
+  free(buf); free(q_prop);
+}
+
+/* base_hmc::init_stepsize */
+static void init_stepsize(hmc_t *s, const double *q, uint32_t tag_iter) {
+  int D = s->D, direction;
+  uint32_t attempt = 0;
+  double H0, h, delta_H;
+  if (s->eps == 0 || s->eps > 1e7 || isnan(s->eps)) return;
+  memcpy(s->z.q, q, sizeof(double) * (size_t)D);
+  sample_p(s, &s->z, PURP_SS_MOMENTUM, attempt++, tag_iter);
+  update_pg(s, &s->z);
+  H0 = hamil(s, &s->z);
+  leapfrog(s, &s->z, s->eps);
+  h = hamil(s, &s->z);
+  if (isnan(h)) h = INFINITY;
+  delta_H = H0 - h;
+  direction = delta_H > log(0.8) ? 1 : -1;
+  for (;;) {
+    memcpy(s->z.q, q, sizeof(double) * (size_t)D);
+    sample_p(s, &s->z, PURP_SS_MOMENTUM, attempt++, tag_iter);
+    update_pg(s, &s->z);
+    H0 = hamil(s, &s->z);
+    leapfrog(s, &s->z, s->eps);
+    h = hamil(s, &s->z);
+    if (isnan(h)) h = INFINITY;
+    delta_H = H0 - h;
+    if (direction == 1 && !(delta_H > log(0.8))) break;
+    else if (direction == -1 && !(delta_H < log(0.8))) break;
+    else s->eps = direction == 1 ? 2 * s->eps : 0.5 * s->eps;
+    if (s->eps > 1e7 || s->eps == 0) break; /* upstream throws; the caller flags the chain */
+  }
+}
+
+/* stepsize_adaptation.hpp */
+typedef struct { double mu, delta, gamma, kappa, t0, counter, s_bar, x_bar; } da_t;
+static void da_restart(da_t *a) { a->counter = 0; a->s_bar = 0; a->x_bar = 0; }
+static void da_learn(da_t *a, double *eps, double adapt_stat) {
+  double eta, x, x_eta;
+  a->counter += 1;
+  adapt_stat = adapt_stat > 1 ? 1 : adapt_stat;
+  eta = 1.0 / (a->counter + a->t0);
+  a->s_bar = (1.0 - eta) * a->s_bar + eta * (a->delta - adapt_stat);
+  x = a->mu - a->s_bar * sqrt(a->counter) / a->gamma;
+  x_eta = pow(a->counter, -a->kappa);
+  a->x_bar = (1.0 - x_eta) * a->x_bar + x_eta * x;
+  *eps = exp(x);
+}
+
+/* windowed_adaptation.hpp + var_adaptation.hpp + welford_var_estimator.hpp */
+typedef struct {
+  unsigned num_warmup, init_buffer, term_buffer, base_window;
+  unsigned window_counter, window_size, next_window;
+  double n;
+  double *m, *m2;
+} wa_t;
+static void wa_restart(wa_t *w) {
+  w->window_counter = 0;
+  w->window_size = w->base_window;
+  w->next_window = w->init_buffer + w->window_size - 1;
+}
+static void wa_setup(wa_t *w, unsigned num_warmup, unsigned init_buffer, unsigned term_buffer,
+                     unsigned base_window) {
+  w->num_warmup = 0; w->init_buffer = 0; w->term_buffer = 0; w->base_window = 0;
+  wa_restart(w);
+  if (num_warmup < 20) return; /* "No variance estimation is performed for num_warmup < 20" */
+  if (init_buffer + base_window + term_buffer > num_warmup) {
+    num_warmup = num_warmup; /* keep */
+    init_buffer = (unsigned)(0.15 * num_warmup);
+    term_buffer = (unsigned)(0.1 * num_warmup);
+    base_window = num_warmup - (init_buffer + term_buffer);
+  }
+  w->num_warmup = num_warmup;
+  w->init_buffer = init_buffer;
+  w->term_buffer = term_buffer;
+  w->base_window = base_window;
+  wa_restart(w);
+}
+static int wa_in_window(const wa_t *w) {
+  return (w->window_counter >= w->init_buffer) && (w->window_counter < w->num_warmup - w->term_buffer) &&
+         (w->window_counter != w->num_warmup);
+}
+static int wa_end_window(const wa_t *w) {
+  return (w->window_counter == w->next_window) && (w->window_counter != w->num_warmup);
+}
+static void wa_compute_next(wa_t *w) {
+  unsigned boundary;
+  if (w->next_window == w->num_warmup - w->term_buffer - 1) return;
+  w->window_size *= 2;
+  w->next_window = w->window_counter + w->window_size;
+  if (w->next_window == w->num_warmup - w->term_buffer - 1) return;
+  boundary = w->next_window + 2 * w->window_size;
+  if (boundary >= w->num_warmup - w->term_buffer) w->next_window = w->num_warmup - w->term_buffer - 1;
+}
+static int wa_learn_variance(wa_t *w, double *var, const double *q, int D) {
+  int i;
+  if (wa_in_window(w)) {
+    w->n += 1;
+    for (i = 0; i < D; ++i) {
+      double delta = q[i] - w->m[i];
+      w->m[i] += delta / w->n;
+      w->m2[i] += (q[i] - w->m[i]) * delta;
+    }
+  }
+  if (wa_end_window(w)) {
+    double n = w->n;
+    wa_compute_next(w);
+    for (i = 0; i < D; ++i) {
+      double v = var[i];
+      if (n > 1) v = w->m2[i] / (n - 1.0);
+      var[i] = (n / (n + 5.0)) * v + 1e-3 * (5.0 / (n + 5.0));
+    }
+    w->n = 0;
+    memset(w->m, 0, sizeof(double) * (size_t)D);
+    memset(w->m2, 0, sizeof(double) * (size_t)D);
+    ++w->window_counter;
+    return 1;
+  }
+  ++w->window_counter;
+  return 0;
+}
+
+/* services/sample/hmc_nuts_diag_e_adapt.hpp + util/run_adaptive_sampler.hpp
+ * + util/initialize.hpp */
+int32_t orc_nuts_generic(orc_density_fn fn, void *ctx, int32_t D, const orc_nuts_cfg *cfg,
+                         uint32_t gene_id, uint32_t chain_id, const double *q_init,
+                         int32_t save_warmup, double *draws, double *inv_metric_out,
+                         double *stepsize_out, int64_t *n_grad_out) {
+  hmc_t s;
+  da_t da;
+  wa_t wa;
+  int i, it, row = 0, ok = 0;
+  double *q = (double *)calloc((size_t)D, sizeof(double));
+  draw_info_t info;
+
+  memset(&s, 0, sizeof(s));
+  s.D = D; s.fn = fn; s.ctx = ctx;
+  s.inv_metric = (double *)malloc(sizeof(double) * (size_t)D);
+  for (i = 0; i < D; ++i) s.inv_metric[i] = 1.0;
+  s.eps = cfg->stepsize;
+  s.max_depth = cfg->max_depth;
+  s.max_deltaH = 1000.0;
+  s.rng.seed = cfg->seed; s.rng.chain = chain_id; s.rng.gene = gene_id;
+  s.tmp = (double *)malloc(sizeof(double) * (size_t)D);
+  ps_alloc(&s.z, D);
+
+  /* initialize: uniform(-R,R) on the unconstrained scale, <=100 attempts */
+  if (q_init) {
+    double lp;
+    memcpy(q, q_init, sizeof(double) * (size_t)D);
+    lp = fn(ctx, q, s.tmp);
+    s.n_grad++;
+    ok = isfinite(lp);
+    for (i = 0; ok && i < D; ++i) ok = isfinite(s.tmp[i]);
+  } else {
+    uint32_t attempt;
+    for (attempt = 0; attempt < 100 && !ok; ++attempt) {
+      double lp;
+      for (i = 0; 2 * i < D; ++i) {
+        double u0, u1;
+        rng_u2(&s.rng, PURP_INIT, 0, attempt, (uint32_t)i, &u0, &u1);
+        q[2 * i] = cfg->init_radius * (2.0 * u0 - 1.0);
+        if (2 * i + 1 < D) q[2 * i + 1] = cfg->init_radius * (2.0 * u1 - 1.0);
+      }
+      lp = fn(ctx, q, s.tmp);
+      s.n_grad++;
+      ok = isfinite(lp);
+      for (i = 0; ok && i < D; ++i) ok = isfinite(s.tmp[i]);
+    }
+  }
+  if (!ok) {
+    free(q); free(s.inv_metric); free(s.tmp); ps_free(&s.z);
+    if (n_grad_out) *n_grad_out = s.n_grad;
+    return 1;
+  }
+
+  da.mu = log(10 * cfg->stepsize);
+  da.delta = cfg->delta; da.gamma = cfg->gamma; da.kappa = cfg->kappa; da.t0 = cfg->t0;
+  da_restart(&da);
+  wa.m = (double *)calloc((size_t)D, sizeof(double));
+  wa.m2 = (double *)calloc((size_t)D, sizeof(double));
+  wa.n = 0;
+  wa_setup(&wa, (unsigned)cfg->num_warmup, (unsigned)cfg->init_buffer, (unsigned)cfg->term_buffer,
+           (unsigned)cfg->window);
+
+  init_stepsize(&s, q, 0);
+
+  for (it = 0; it < cfg->num_warmup + cfg->num_samples; ++it) {
+    int warm = it < cfg->num_warmup;
+    if (it == cfg->num_warmup) s.eps = exp(da.x_bar); /* complete_adaptation */
+    nuts_transition(&s, q, (uint32_t)it, &info);
+    if (warm) {
+      int update;
+      da_learn(&da, &s.eps, info.accept_stat);
+      update = wa_learn_variance(&wa, s.inv_metric, q, D);
+      if (update) {
+        init_stepsize(&s, q, (uint32_t)it + 1);
+        da.mu = log(10 * s.eps);
+        da_restart(&da);
+      }
+    }
+    if (draws && (!warm || save_warmup)) {
+      double *r = draws + (size_t)row * (size_t)(7 + D);
+      r[0] = info.lp; r[1] = info.accept_stat; r[2] = info.stepsize; r[3] = info.treedepth;
+      r[4] = info.n_leapfrog; r[5] = info.divergent; r[6] = info.energy;
+      memcpy(r + 7, q, sizeof(double) * (size_t)D);
+      ++row;
+    }
+  }
+  if (cfg->num_samples == 0 && cfg->num_warmup >= 0) s.eps = exp(da.x_bar);
+  if (inv_metric_out) memcpy(inv_metric_out, s.inv_metric, sizeof(double) * (size_t)D);
+  if (stepsize_out) *stepsize_out = s.eps;
+  if (n_grad_out) *n_grad_out = s.n_grad;
+  free(q); free(s.inv_metric); free(s.tmp); ps_free(&s.z); free(wa.m); free(wa.m2);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Splotch density bound to the sampler                                */
+/* ------------------------------------------------------------------ */
+static double splotch_density(void *ctx, const double *q, double *grad) {
+  return orc_log_prob_grad((const orc_data *)ctx, q, grad, 1);
+}
+
+int32_t orc_nuts_run(const orc_data *d, const orc_nuts_cfg *cfg, uint32_t gene_id, uint32_t chain_id,
+                     const double *q_init, int32_t save_warmup, double *draws,
+                     double *inv_metric_out, double *stepsize_out, int64_t *n_grad_out) {
+  return orc_nuts_generic(splotch_density, (void *)d, orc_dim(d), cfg, gene_id, chain_id, q_init,
+                          save_warmup, draws, inv_metric_out, stepsize_out, n_grad_out);
+}
+
+void orc_leapfrog_fixed(const orc_data *d, const double *theta0, const double *p0,
+                        const double *inv_metric, double eps, int32_t n_steps, double *theta_out,
+                        double *p_out, double *H_out, double *traj) {
+  hmc_t s;
+  int D = orc_dim(d), i, n;
+  memset(&s, 0, sizeof(s));
+  s.D = D; s.fn = splotch_density; s.ctx = (void *)d;
+  s.inv_metric = (double *)malloc(sizeof(double) * (size_t)D);
+  memcpy(s.inv_metric, inv_metric, sizeof(double) * (size_t)D);
+  s.tmp = (double *)malloc(sizeof(double) * (size_t)D);
+  ps_alloc(&s.z, D);
+  memcpy(s.z.q, theta0, sizeof(double) * (size_t)D);
+  memcpy(s.z.p, p0, sizeof(double) * (size_t)D);
+  update_pg(&s, &s.z);
+  for (n = 0;; ++n) {
+    if (traj) {
+      double *r = traj + (size_t)n * (size_t)(2 * D + 1);
+      for (i = 0; i < D; ++i) { r[i] = s.z.q[i]; r[D + i] = s.z.p[i]; }
+      r[2 * D] = hamil(&s, &s.z);
+    }
+    if (n == n_steps) break;
+    leapfrog(&s, &s.z, eps);
+  }
+  if (theta_out) memcpy(theta_out, s.z.q, sizeof(double) * (size_t)D);
+  if (p_out) memcpy(p_out, s.z.p, sizeof(double) * (size_t)D);
+  if (H_out) *H_out = hamil(&s, &s.z);
+  free(s.inv_metric); free(s.tmp); ps_free(&s.z);
+}
+
+/* ------------------------------------------------------------------ */
+/* gene-parallel batches (CPU baseline; one thread per gene-chain)     */
+/* ------------------------------------------------------------------ */
+int64_t orc_nuts_batch(const orc_data *shared, const int32_t *counts, const double *prior_mean,
+                       const double *prior_std, int32_t G, int32_t n_chains, const orc_nuts_cfg *cfg,
+                       uint32_t gene_id0, int32_t n_threads, double *draws, int32_t *status) {
+  int64_t total = 0;
+  int N = orc_num_spots(shared), D = orc_dim(shared), K = shared->family == 1 ? shared->N_celltypes : 1;
+  int w;
+  (void)n_threads;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic) reduction(+ : total)
+#endif
+  for (w = 0; w < G * n_chains; ++w) {
+    int g = w / n_chains, c = w % n_chains;
+    orc_data d = *shared;
+    int64_t ng = 0;
+    int32_t st;
+    double *out = draws ? draws + ((size_t)w * (size_t)cfg->num_samples) * (size_t)(7 + D) : NULL;
+    d.counts = counts + (size_t)g * (size_t)N;
+    if (prior_mean) d.beta_prior_mean = prior_mean + (size_t)g * (size_t)K;
+    if (prior_std) d.beta_prior_std = prior_std + (size_t)g * (size_t)K;
+    st = orc_nuts_run(&d, cfg, gene_id0 + (uint32_t)g, (uint32_t)c + 1u, NULL, 0, out, NULL, NULL, &ng);
+    if (status) status[w] = st;
+    total += ng;
+  }
+  return total;
+}
+
+void orc_log_prob_grad_batch(const orc_data *shared, const int32_t *counts, const double *prior_mean,
+                             const double *prior_std, int32_t G, const double *theta, int32_t B,
+                             const int32_t *gene_of, double *lp, double *grad, int32_t jacobian,
+                             int32_t n_threads) {
+  int N = orc_num_spots(shared), D = orc_dim(shared), K = shared->family == 1 ? shared->N_celltypes : 1;
+  int w;
+  (void)G; (void)n_threads;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic)
+#endif
+  for (w = 0; w < B; ++w) {
+    int g = gene_of ? gene_of[w] : w;
+    orc_data d = *shared;
+    d.counts = counts + (size_t)g * (size_t)N;
+    if (prior_mean) d.beta_prior_mean = prior_mean + (size_t)g * (size_t)K;
+    if (prior_std) d.beta_prior_std = prior_std + (size_t)g * (size_t)K;
+    lp[w] = orc_log_prob_grad(&d, theta + (size_t)w * (size_t)D, grad ? grad + (size_t)w * (size_t)D : NULL,
+                              jacobian);
+  }
+}
