@@ -1060,3 +1060,22 @@ void orc_log_prob_grad_batch(const orc_data *shared, const int32_t *counts, cons
                               jacobian);
   }
 }
+
+/* exported density callback (ctx = const orc_data*) so that test harnesses can drive other
+ * samplers with exactly this density */
+double orc_splotch_density(void *ctx, const double *q, double *grad) { return splotch_density(ctx, q, grad); }
+
+static double gauss_density(void *ctx, const double *q, double *grad) {
+  /* ctx: double[1 + D]: D, then standard deviations */
+  const double *c = (const double *)ctx;
+  int D = (int)c[0], i;
+  double lp = 0.0;
+  for (i = 0; i < D; ++i) {
+    double z = q[i] / c[1 + i];
+    lp += -0.5 * z * z;
+    grad[i] = -z / c[1 + i];
+  }
+  return lp;
+}
+/* independent-normal test density: ctx = {D, sd_1..sd_D} */
+double orc_gauss_density(void *ctx, const double *q, double *grad) { return gauss_density(ctx, q, grad); }

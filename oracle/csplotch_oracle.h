@@ -80,6 +80,9 @@ int32_t orc_num_outputs(const orc_data *d);
 
 /* lp (propto=true) and gradient at unconstrained theta; returns lp. grad may be NULL. */
 double orc_log_prob_grad(const orc_data *d, const double *theta, double *grad, int32_t jacobian);
+/* density callbacks for orc_nuts_generic / test harnesses */
+double orc_splotch_density(void *ctx, const double *q, double *grad);
+double orc_gauss_density(void *ctx, const double *q, double *grad);
 
 /* constrained parameters + transformed parameters in Stan CSV column order */
 void orc_write_array(const orc_data *d, const double *theta, double *out);

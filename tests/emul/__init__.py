@@ -1,0 +1,56 @@
+"""TEST INFRASTRUCTURE: host build of the product's sampler control logic (nuts_core.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = os.path.join(_HERE, "libemul.so")
+
+
+class NutsConfig(C.Structure):
+    _fields_ = [("num_warmup", C.c_int32), ("num_samples", C.c_int32), ("max_depth", C.c_int32),
+                ("delta", C.c_double), ("gamma", C.c_double), ("kappa", C.c_double), ("t0", C.c_double),
+                ("init_buffer", C.c_int32), ("term_buffer", C.c_int32), ("window", C.c_int32),
+                ("init_radius", C.c_double), ("stepsize", C.c_double), ("seed", C.c_uint32)]
+
+
+def build():
+    srcs = [os.path.join(_HERE, "emul.cpp"), os.path.join(ROOT, "csplotch_b200", "csrc", "nuts_core.h"),
+            os.path.join(ROOT, "csplotch_b200", "csrc", "philox.h")]
+    if (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-I" + os.path.join(ROOT, "csplotch_b200", "csrc"), "-o", _LIB, srcs[0]])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.emul_nuts_run.restype = C.c_int
+    return _lib
+
+
+def nuts_run(fn_ptr, ctx_ptr, D, ocfg, gene_id=0, chain_id=1, q_init=None, chunk=0):
+    """fn_ptr: C function pointer double(void*, const double*, double*); ocfg: oracle._NutsCfg"""
+    cfg = NutsConfig(ocfg.num_warmup, ocfg.num_samples, ocfg.max_depth, ocfg.delta, ocfg.gamma, ocfg.kappa,
+                     ocfg.t0, ocfg.init_buffer, ocfg.term_buffer, ocfg.window, ocfg.init_radius,
+                     ocfg.stepsize, ocfg.seed)
+    draws = np.zeros((ocfg.num_samples, 7 + D))
+    inv_m = np.empty(D)
+    eps = C.c_double(0)
+    nl = C.c_longlong(0)
+    ng = C.c_longlong(0)
+    qi = np.ascontiguousarray(q_init, dtype=np.float64) if q_init is not None else None
+    st = lib().emul_nuts_run(fn_ptr, ctx_ptr, C.c_int(D), C.byref(cfg), C.c_uint32(gene_id),
+                             C.c_uint32(chain_id), qi.ctypes.data_as(C.c_void_p) if qi is not None else None,
+                             C.c_int(chunk), draws.ctypes.data_as(C.c_void_p), inv_m.ctypes.data_as(C.c_void_p),
+                             C.byref(eps), C.byref(nl), C.byref(ng))
+    return dict(status=st, draws=draws, inv_metric=inv_m, stepsize=eps.value, n_leapfrog=nl.value,
+                n_grad=ng.value)

@@ -1,0 +1,75 @@
+"""The product's sampler control logic (csplotch_b200/csrc/nuts_core.h: iterative tree with a
+vector pool, reservoir proposal, windowed adaptation) run on the host against the oracle's
+recursive restatement of Stan's base_nuts: same Philox stream => the same draws."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from csplotch_b200 import synth
+from tests import emul
+
+
+def _gauss_ctx(sd):
+    arr = np.concatenate([[len(sd)], sd]).astype(np.float64)
+    return arr, arr.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("nw,ns", [(0, 30), (10, 20), (60, 40), (150, 50), (200, 100)])
+def test_gaussian_draw_for_draw(nw, ns):
+    D = 7
+    sd = np.linspace(0.3, 4.0, D)
+    arr, ctx = _gauss_ctx(sd)
+    cfg = oracle.nuts_cfg(nw, ns, seed=11)
+    fn = C.cast(oracle.lib().orc_gauss_density, C.c_void_p)
+    want = oracle.lib()
+    draws_o = np.zeros((ns, 7 + D)); inv_o = np.empty(D); eps_o = C.c_double(0); ng = C.c_int64(0)
+    st = want.orc_nuts_generic(fn, ctx, C.c_int32(D), C.byref(cfg), C.c_uint32(3), C.c_uint32(2), None,
+                               C.c_int32(0), draws_o.ctypes.data_as(C.c_void_p),
+                               inv_o.ctypes.data_as(C.c_void_p), C.byref(eps_o), C.byref(ng))
+    assert st == 0
+    got = emul.nuts_run(fn, ctx, D, cfg, gene_id=3, chain_id=2, chunk=7)
+    assert got["status"] == 0
+    assert np.array_equal(got["draws"][:, 3:6], draws_o[:, 3:6])          # treedepth, n_leapfrog, divergent
+    assert np.allclose(got["draws"], draws_o, rtol=1e-9, atol=1e-9)
+    assert np.allclose(got["inv_metric"], inv_o, rtol=1e-12)
+    assert abs(got["stepsize"] - eps_o.value) < 1e-12 * eps_o.value
+
+
+@pytest.mark.parametrize("family,n_levels,zi,car", [
+    ("comp_splotch_stan_model", 3, 1, 1),
+    ("splotch_stan_model", 2, 0, 1),
+    ("splotch_stan_model_csr", 2, 1, 1),
+    ("splotch_stan_model", 1, 1, 0),
+])
+def test_splotch_draw_for_draw(family, n_levels, zi, car):
+    shared = synth.shared_tiny(seed=5, family=family, n_levels=n_levels, zi=zi, car=car)
+    genes = synth.simulate_counts(shared, 1, 8)
+    o = oracle.Oracle(synth.gene_dict(shared, genes, 0), family)
+    cfg = oracle.nuts_cfg(40, 25, seed=4)
+    want = o.nuts(cfg, gene_id=9, chain_id=1)
+    fn = C.cast(oracle.lib().orc_splotch_density, C.c_void_p)
+    got = emul.nuts_run(fn, C.cast(C.pointer(o.c), C.c_void_p), o.dim, cfg, gene_id=9, chain_id=1, chunk=13)
+    assert want["status"] == 0 and got["status"] == 0
+    assert np.array_equal(got["draws"][:, 3:6], want["draws"][:, 3:6])
+    assert np.allclose(got["draws"], want["draws"], rtol=1e-8, atol=1e-8)
+    assert abs(got["stepsize"] - want["stepsize"]) < 1e-10 * want["stepsize"]
+
+
+def test_max_depth_and_divergence_paths():
+    """tiny step size forces max_depth; a huge one forces divergences; both must agree with the oracle."""
+    D = 5
+    sd = np.array([1e-2, 1.0, 1.0, 1.0, 50.0])
+    arr, ctx = _gauss_ctx(sd)
+    fn = C.cast(oracle.lib().orc_gauss_density, C.c_void_p)
+    for stepsize, md in ((1e-3, 6), (1.0, 10)):
+        cfg = oracle.nuts_cfg(0, 40, seed=2, max_depth=md, stepsize=stepsize)
+        draws_o = np.zeros((40, 7 + D)); ng = C.c_int64(0)
+        q0 = np.full(D, 0.1)
+        oracle.lib().orc_nuts_generic(fn, ctx, C.c_int32(D), C.byref(cfg), C.c_uint32(0), C.c_uint32(1),
+                                      q0.ctypes.data_as(C.c_void_p), C.c_int32(0),
+                                      draws_o.ctypes.data_as(C.c_void_p), None, None, C.byref(ng))
+        got = emul.nuts_run(fn, ctx, D, cfg, gene_id=0, chain_id=1, q_init=q0)
+        assert np.array_equal(got["draws"][:, 3:6], draws_o[:, 3:6])
+        assert np.allclose(got["draws"], draws_o, rtol=1e-9, atol=1e-9)
