@@ -1,0 +1,427 @@
+"""Host-side mirror of the reference's interface for the sampling path.
+
+Reference call sites this stands in for (relative to /root/reference):
+  * bin/splotch:129-133      `BINARY sample num_samples=N num_warmup=N random id=CHAIN data file=… output file=…`
+  * simulation/fitting.py:35-51   `pystan.StanModel(file).sampling(data=dict, iter=…, chains=…)`,
+                                  `fit.extract(permuted=True)['beta_level_1']`
+Everything numerical happens in libcsplotch_b200.so (CUDA, sm_100a) through the C ABI of
+include/csplotch.h; this module only marshals numpy arrays.  No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import CsplotchError, Dims, NutsCfg, SharedDesc, check
+
+FAMILIES = {
+    "splotch_stan_model": 0,
+    "comp_splotch_stan_model": 1,
+    "splotch_stan_model_csr": 2,
+}
+
+
+def family_from_binary(path_or_name) -> int:
+    """`-b BINARY` of bin/splotch: the basename selects the model family."""
+    if isinstance(path_or_name, int):
+        return path_or_name
+    name = os.path.basename(str(path_or_name))
+    for suffix in (".stan", ".exe"):
+        if name.endswith(suffix):
+            name = name[: -len(suffix)]
+    if name not in FAMILIES:
+        raise ValueError("unknown Splotch binary %r; expected one of %s" % (name, sorted(FAMILIES)))
+    return FAMILIES[name]
+
+
+def _i32(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int32).reshape(-1))
+
+
+def _f64(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class Model:
+    """Gene-shared covariates (the data{} block minus `counts`, `beta_prior_*`) resident on the GPU."""
+
+    def __init__(self, data: dict, family):
+        self.lib = _lib.lib()
+        _lib.require_gpu()
+        fam = family_from_binary(family)
+        self.family = fam
+        d = data
+        k = {}
+        k["N_spots"] = _i32(np.atleast_1d(d["N_spots"]))
+        N = int(k["N_spots"].sum())
+        K = int(d.get("N_celltypes", 1)) if fam == 1 else 1
+        car = int(d.get("car", 0))
+        k["l2"] = _i32(d.get("level_2_mapping", []))
+        k["l3"] = _i32(d.get("level_3_mapping", []))
+        k["tm"] = _i32(np.atleast_1d(d["tissue_mapping"]))
+        k["sf"] = _f64(d["size_factors"])
+        k["D"] = _i32(d["D"])
+        if k["sf"].size != N or k["D"].size != N:
+            raise CsplotchError("size_factors / D must have sum(N_spots) entries")
+        k["E"] = None
+        if fam == 1:
+            E = np.asarray(d["E"], dtype=np.float64)
+            if E.size != N * K:
+                raise CsplotchError("E must be (sum(N_spots), N_celltypes)")
+            k["E"] = np.ascontiguousarray(E.reshape(N, K)).reshape(-1)
+        W_n = int(np.atleast_1d(d.get("W_n", [0]))[0]) if car and np.size(d.get("W_n", [])) else 0
+        k["W"] = k["U"] = k["V"] = k["Ds"] = k["eig"] = None
+        if car:
+            if "W_sparse" in d and np.size(d["W_sparse"]):
+                k["W"] = _i32(np.asarray(d["W_sparse"]).reshape(W_n, 2))
+            if "U" in d and np.size(d["U"]):
+                k["U"] = _i32(d["U"])
+                k["V"] = _i32(d["V"])
+                if k["U"].size != N + 1:
+                    raise CsplotchError("U must have N+1 entries")
+                if not W_n:
+                    W_n = k["V"].size // 2
+            k["Ds"] = _f64(d["D_sparse"])
+            k["eig"] = _f64(d["eig_values"])
+            if k["Ds"].size != N or k["eig"].size != N:
+                raise CsplotchError("D_sparse / eig_values must have sum(N_spots) entries")
+        self._keep = k
+        desc = SharedDesc(
+            fam, int(d["N_tissues"]), _p(k["N_spots"]), int(d["N_covariates"]), K,
+            int(d["N_level_1"]), int(d.get("N_level_2", 0)), int(d.get("N_level_3", 0)),
+            int(d.get("zi", 0)), car, int(d.get("nb", 0)) if fam == 1 else 0,
+            _p(k["l2"]), _p(k["l3"]), _p(k["tm"]), _p(k["sf"]), _p(k["D"]), _p(k["E"]),
+            W_n, _p(k["W"]), _p(k["U"]), _p(k["V"]), _p(k["Ds"]), _p(k["eig"]))
+        h = C.c_void_p()
+        check(self.lib.csplotch_model_create(C.byref(desc), C.byref(h)))
+        self.h = h
+        dims = Dims()
+        check(self.lib.csplotch_model_dims(self.h, C.byref(dims)))
+        self.N, self.dim, self.n_beta, self.n_scalar = dims.N, dims.dim, dims.n_beta, dims.n_scalar
+        self.n_small, self.n_outputs = dims.n_small, dims.n_outputs
+        self.K = K
+        self.C = int(d["N_covariates"])
+        self.levels = (int(d["N_level_1"]), int(d.get("N_level_2", 0)), int(d.get("N_level_3", 0)))
+        self.car, self.zi = car, int(d.get("zi", 0))
+        self.level_2_mapping = np.asarray(d.get("level_2_mapping", []), dtype=np.int64).reshape(-1)
+        self.level_3_mapping = np.asarray(d.get("level_3_mapping", []), dtype=np.int64).reshape(-1)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.csplotch_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- names / shapes of the Stan CSV columns ----------------------------
+    def column_names(self):
+        L1, L2, L3 = self.levels
+        L = L1 + L2 + L3
+        N, Cc, K = self.N, self.C, self.K
+        comp = self.family == 1
+        cols = []
+        if self.car:
+            cols += ["psi.%d" % (i + 1) for i in range(N)]
+        if comp:
+            cols += ["beta_raw.%d.%d.%d" % (i + 1, j + 1, k + 1) for k in range(K) for j in range(Cc) for i in range(L)]
+        else:
+            cols += ["beta_raw.%d.%d" % (i + 1, j + 1) for j in range(Cc) for i in range(L)]
+        if self.car:
+            cols += ["tau.1", "a.1"]
+        cols += ["sigma"]
+        if L2:
+            cols += ["sigma_level_2.1"]
+        if L3:
+            cols += ["sigma_level_3.1"]
+        if self.zi:
+            cols += ["theta.1"]
+        cols += ["noise_raw.%d" % (i + 1) for i in range(N)]
+        cols += ["log_lambda.%d" % (i + 1) for i in range(N)]
+        for lev, nr in ((1, L1), (2, L2), (3, L3)):
+            if comp:
+                cols += ["beta_level_%d.%d.%d.%d" % (lev, i + 1, j + 1, k + 1)
+                         for k in range(K) for j in range(Cc) for i in range(nr)]
+            else:
+                cols += ["beta_level_%d.%d.%d" % (lev, i + 1, j + 1) for j in range(Cc) for i in range(nr)]
+        assert len(cols) == self.n_outputs
+        return cols
+
+
+class Batch:
+    """counts (+ beta priors) of G genes on the GPU.  counts: (G, N) int; priors: (G, K) for comp."""
+
+    def __init__(self, model: Model, counts, beta_prior_mean=None, beta_prior_std=None, gene_id0: int = 0):
+        self.model = model
+        self.lib = model.lib
+        c = np.ascontiguousarray(np.asarray(counts, dtype=np.int32).reshape(-1, model.N))
+        self.G = c.shape[0]
+        pm = ps = None
+        if model.family == 1:
+            if beta_prior_mean is None or beta_prior_std is None:
+                raise CsplotchError("comp_splotch_stan_model needs beta_prior_mean / beta_prior_std")
+            pm = np.ascontiguousarray(np.asarray(beta_prior_mean, dtype=np.float64).reshape(self.G, model.K))
+            ps = np.ascontiguousarray(np.asarray(beta_prior_std, dtype=np.float64).reshape(self.G, model.K))
+        self.beta_prior_mean, self.beta_prior_std = pm, ps
+        h = C.c_void_p()
+        check(self.lib.csplotch_batch_create(model.h, _p(c), _p(pm) if pm is not None else None,
+                                             _p(ps) if ps is not None else None, C.c_int32(self.G),
+                                             C.c_uint32(gene_id0), C.byref(h)))
+        self.h = h
+        self.gene_id0 = gene_id0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.csplotch_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # model.log_prob / grad_log_prob of the stanc-generated class (propto=true)
+    def log_prob_grad(self, theta, gene_of=None, jacobian=True, want_grad=True):
+        m = self.model
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(-1, m.dim))
+        B = th.shape[0]
+        go = _i32(gene_of) if gene_of is not None else None
+        lp = np.empty(B)
+        grad = np.empty((B, m.dim)) if want_grad else None
+        check(self.lib.csplotch_log_prob_grad(self.h, _p(th), _p(go) if go is not None else None, C.c_int32(B),
+                                              _p(lp), _p(grad) if want_grad else None,
+                                              C.c_int32(1 if jacobian else 0)))
+        return (lp, grad) if want_grad else lp
+
+    def write_array(self, theta, gene_of=None):
+        m = self.model
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(-1, m.dim))
+        B = th.shape[0]
+        go = _i32(gene_of) if gene_of is not None else None
+        out = np.empty((B, m.n_outputs))
+        check(self.lib.csplotch_write_array(self.h, _p(th), _p(go) if go is not None else None, C.c_int32(B), _p(out)))
+        return out
+
+    def leapfrog_fixed(self, theta0, p0, inv_metric, eps, n_steps, gene_of=None):
+        m = self.model
+        th = np.ascontiguousarray(np.asarray(theta0, dtype=np.float64).reshape(-1, m.dim))
+        B = th.shape[0]
+        p = np.ascontiguousarray(np.asarray(p0, dtype=np.float64).reshape(B, m.dim))
+        mi = np.ascontiguousarray(np.asarray(inv_metric, dtype=np.float64).reshape(B, m.dim))
+        go = _i32(gene_of) if gene_of is not None else None
+        tho, po, H = np.empty((B, m.dim)), np.empty((B, m.dim)), np.empty(B)
+        check(self.lib.csplotch_leapfrog_fixed(self.h, _p(th), _p(p), _p(mi), _p(go) if go is not None else None,
+                                               C.c_int32(B), C.c_double(eps), C.c_int32(n_steps), _p(tho), _p(po),
+                                               _p(H)))
+        return tho, po, H
+
+
+def nuts_cfg(num_warmup, num_samples, num_chains=4, seed=0, keep_draws=False, **kw) -> NutsCfg:
+    cfg = NutsCfg()
+    _lib.lib().csplotch_nuts_cfg_default(C.byref(cfg))
+    cfg.num_warmup, cfg.num_samples, cfg.num_chains = int(num_warmup), int(num_samples), int(num_chains)
+    cfg.seed = int(seed) & 0xFFFFFFFF
+    cfg.keep_draws = 1 if keep_draws else 0
+    for key, val in kw.items():
+        if not hasattr(cfg, key):
+            raise TypeError("unknown sampler option %r" % key)
+        setattr(cfg, key, val)
+    return cfg
+
+
+class Sampler:
+    """hmc_nuts_diag_e_adapt for every gene x chain of a Batch (one CTA per gene-chain)."""
+
+    def __init__(self, batch: Batch, cfg: NutsCfg, theta_init=None):
+        self.batch, self.cfg, self.lib = batch, cfg, batch.lib
+        self.model = batch.model
+        h = C.c_void_p()
+        check(self.lib.csplotch_sampler_create(batch.h, C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.G, self.nch = batch.G, cfg.num_chains
+        if theta_init is not None:
+            ti = np.ascontiguousarray(np.asarray(theta_init, dtype=np.float64).reshape(self.G, self.nch, self.model.dim))
+            check(self.lib.csplotch_sampler_init(self.h, _p(ti)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.csplotch_sampler_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def advance(self, n_iter: int, sync: bool = True):
+        check(self.lib.csplotch_sampler_advance(self.h, C.c_int32(n_iter), C.c_int32(1 if sync else 0)))
+
+    def sync(self):
+        check(self.lib.csplotch_sampler_sync(self.h))
+
+    def run(self, chunk: int | None = None):
+        total = self.cfg.num_warmup + self.cfg.num_samples
+        chunk = total if not chunk else chunk
+        done = 0
+        while done < total:
+            n = min(chunk, total - done)
+            self.advance(n, sync=True)
+            done += n
+        return self
+
+    def last_ms(self) -> float:
+        ms = C.c_float(0)
+        check(self.lib.csplotch_sampler_last_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def counters(self):
+        a, b, c, d = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(self.lib.csplotch_sampler_counters(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(n_leapfrog=a.value, n_grad=b.value, n_divergent=c.value, n_launches=d.value)
+
+    def status(self):
+        st = np.zeros((self.G, self.nch), dtype=np.int32)
+        it = np.zeros((self.G, self.nch), dtype=np.int32)
+        check(self.lib.csplotch_sampler_status(self.h, _p(st), _p(it)))
+        return st, it
+
+    def draws(self):
+        """(diag [G,ch,S,7], small [G,ch,S,n_small] unconstrained beta_raw|scalars, n_draws [G,ch])"""
+        ns = self.cfg.num_samples
+        diag = np.empty((self.G, self.nch, ns, 7))
+        small = np.empty((self.G, self.nch, ns, self.model.n_small))
+        nd = np.zeros((self.G, self.nch), dtype=np.int32)
+        check(self.lib.csplotch_sampler_get_draws(self.h, _p(diag), _p(small), _p(nd)))
+        return diag, small, nd
+
+    def theta_draws(self):
+        out = np.empty((self.G, self.nch, self.cfg.num_samples, self.model.dim))
+        check(self.lib.csplotch_sampler_get_theta_draws(self.h, _p(out)))
+        return out
+
+    def state(self):
+        th = np.empty((self.G, self.nch, self.model.dim))
+        eps = np.empty((self.G, self.nch))
+        mi = np.empty((self.G, self.nch, self.model.dim))
+        check(self.lib.csplotch_sampler_get_state(self.h, _p(th), _p(eps), _p(mi)))
+        return th, eps, mi
+
+    def spot_summaries(self):
+        """dict of (G, N) arrays: mean/std (ddof=0, pooled over chains) of log_lambda, lambda, psi."""
+        N = self.model.N
+        arrs = [np.empty((self.G, N)) for _ in range(6)]
+        check(self.lib.csplotch_sampler_get_spot_summaries(self.h, *[_p(a) for a in arrs]))
+        keys = ["log_lambda/mean", "log_lambda/std", "lambda/mean", "lambda/std", "psi/mean", "psi/std"]
+        out = dict(zip(keys, arrs))
+        if not self.model.car:
+            out.pop("psi/mean"); out.pop("psi/std")
+        return out
+
+    # ---- constrained small block: what read_stan_csv would give for the non-spot variables ------
+    def extract_small(self):
+        """Per gene g: dict var -> array with the sample axis first, chains concatenated chain-major
+        (the order of `combined_<g>.csv`, bin/splotch:138-140).  beta_level_k: (S, L_k, C[, K])."""
+        m = self.model
+        diag, small, nd = self.draws()
+        L1, L2, L3 = m.levels
+        L, Cc, K = L1 + L2 + L3, m.C, m.K
+        G, nch, ns = self.G, self.nch, self.cfg.num_samples
+        raw = small[..., : m.n_beta].reshape(G, nch * ns, L, Cc, K)
+        sc = small[..., m.n_beta:].reshape(G, nch * ns, m.n_scalar)
+        names = []
+        if m.car:
+            names += ["tau", "a"]
+        names += ["sigma"]
+        if L2:
+            names += ["sigma_level_2"]
+        if L3:
+            names += ["sigma_level_3"]
+        if m.zi:
+            names += ["theta"]
+        out = {}
+        for i, nme in enumerate(names):
+            u = sc[..., i]
+            out[nme] = (1.0 / (1.0 + np.exp(-u))) if nme in ("a", "theta") else np.exp(u)
+        if m.family == 1:
+            std = self.batch.beta_prior_std[:, None, None, None, :]
+            mean = self.batch.beta_prior_mean[:, None, None, None, :]
+            b1 = raw[:, :, :L1] * std + mean
+        else:
+            b1 = 2.0 * raw[:, :, :L1]
+        out["beta_level_1"] = b1
+        if L2:
+            b2 = b1[:, :, m.level_2_mapping - 1] + out["sigma_level_2"][..., None, None, None] * raw[:, :, L1:L1 + L2]
+            out["beta_level_2"] = b2
+        if L3:
+            b3 = b2[:, :, m.level_3_mapping - 1] + out["sigma_level_3"][..., None, None, None] * raw[:, :, L1 + L2:]
+            out["beta_level_3"] = b3
+        if m.family != 1:
+            for key in list(out):
+                if key.startswith("beta_level"):
+                    out[key] = out[key][..., 0]
+        out["diag"] = diag.reshape(G, nch * ns, 7)
+        out["n_draws"] = nd
+        return out
+
+
+class Fit:
+    """Result of SplotchModel.sampling(): PyStan-like `extract()` for one gene."""
+
+    def __init__(self, sampler: Sampler, g: int = 0):
+        self.sampler, self.g = sampler, g
+        self._small = sampler.extract_small()
+        self._spots = None
+
+    def extract(self, pars=None, permuted=True):
+        out = {k: v[self.g] for k, v in self._small.items() if k not in ("diag", "n_draws")}
+        out["lp__"] = self._small["diag"][self.g][:, 0]
+        if self.sampler.cfg.keep_draws:
+            m = self.sampler.model
+            th = self.sampler.theta_draws()[self.g].reshape(-1, m.dim)
+            wa = self.sampler.batch.write_array(th, gene_of=np.full(len(th), self.g, dtype=np.int32))
+            cols = m.column_names()
+            i0 = cols.index("log_lambda.1")
+            out["log_lambda"] = wa[:, i0:i0 + m.N]
+            if m.car:
+                out["psi"] = wa[:, :m.N]
+        if pars is not None:
+            pars = [pars] if isinstance(pars, str) else list(pars)
+            out = {k: out[k] for k in pars}
+        return out
+
+    def sampler_diagnostics(self):
+        d = self._small["diag"][self.g]
+        names = ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"]
+        return {n: d[:, i] for i, n in enumerate(names)}
+
+
+class SplotchModel:
+    """Stand-in for `pystan.StanModel(file=…)` / the compiled CmdStan binary of one .stan file."""
+
+    def __init__(self, file=None, model_name=None):
+        self.family = family_from_binary(file if file is not None else model_name)
+
+    def sampling(self, data: dict, iter: int = 2000, chains: int = 4, warmup: int | None = None, seed: int = 0,
+                 keep_draws: bool = False, **control) -> Fit:
+        """PyStan semantics: `iter` counts warm-up + sampling, warm-up defaults to iter // 2."""
+        warmup = iter // 2 if warmup is None else warmup
+        shared = {k: v for k, v in data.items() if k not in ("counts", "beta_prior_mean", "beta_prior_std")}
+        model = Model(shared, self.family)
+        batch = Batch(model, np.asarray(data["counts"])[None, :],
+                      None if self.family != 1 else np.asarray(data["beta_prior_mean"])[None, :],
+                      None if self.family != 1 else np.asarray(data["beta_prior_std"])[None, :])
+        cfg = nuts_cfg(warmup, iter - warmup, chains, seed=seed, keep_draws=keep_draws, **control)
+        s = Sampler(batch, cfg).run()
+        return Fit(s, 0)

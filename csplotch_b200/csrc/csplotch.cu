@@ -1,0 +1,1045 @@
+// csplotch.cu — kernels + C ABI (include/csplotch.h) of the B200-native cSplotch sampling path.
+//
+// Kernels (sm_100a):
+//   k_nuts_advance   persistent; one CTA per gene-chain pulled from an atomic queue; runs the whole
+//                    Stan-compatible adaptive NUTS of nuts_core.h with the fused fp64
+//                    log-density+gradient / leapfrog of device_ops.cuh.
+//   k_lpgrad         stand-alone log_prob_grad (tier-1 parity, roofline B_grad)
+//   k_leapfrog_fixed fixed-step trajectories (tier-2 parity)
+//   small helpers    layout permutation, count repacking, per-gene constants, summaries
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/csplotch.h"
+#include "device_ops.cuh"
+
+using namespace csp;
+
+// ------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(CSPLOTCH_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));         \
+  } while (0)
+
+struct DevBuf {
+  std::vector<void *> ptrs;
+  ~DevBuf() {
+    for (void *p : ptrs) cudaFree(p);
+  }
+  template <class T>
+  cudaError_t alloc(T **out, size_t n) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = (T *)p;
+    return e;
+  }
+  template <class T>
+  cudaError_t upload(T **out, const std::vector<T> &h) {
+    cudaError_t e = alloc(out, h.size());
+    if (e != cudaSuccess) return e;
+    if (!h.empty()) e = cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// opaque handles
+// ------------------------------------------------------------------------------------------------
+struct csplotch_model {
+  DevModel dm;
+  DevBuf buf;
+  int device = 0;
+  int T = 0;
+  std::vector<int> imap;  // internal -> Stan
+  std::vector<int> perm;  // internal spot -> original spot
+  int kt = 1;             // template instantiation (max K)
+  size_t smem_bytes = 0;
+  int n_outputs = 0;
+};
+
+struct csplotch_batch {
+  csplotch_model *m = nullptr;
+  DevBuf buf;
+  int G = 0;
+  uint32_t gene_id0 = 0;
+  int *counts = nullptr;     // [G][Nc] internal spot order
+  double *pm = nullptr;      // [G][K]
+  double *ps = nullptr;
+  double *lgam = nullptr;    // [G]
+  double *nnz = nullptr;     // [G]
+};
+
+struct SamplerDev {
+  ChainScalars *cs;
+  double *q_cur, *minv, *wm, *wm2;  // [W][Di]
+  double *ws;                       // [slots][kPoolVecs + 6][Di]
+  double *diag, *small, *theta, *summ;
+  int *queue;
+  int W, num_chains, n_slots, have_init;
+  uint32_t gene_id0;
+  NutsConfig cfg;
+  const int *counts;
+  const double *pm, *ps, *lgam, *nnz;
+};
+
+struct csplotch_sampler {
+  csplotch_batch *b = nullptr;
+  DevBuf buf;
+  SamplerDev sd;
+  csplotch_nuts_cfg cfg;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  int grid = 0;
+  int64_t launches = 0;
+  ~csplotch_sampler() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_repack_counts(const int *__restrict__ raw, int *__restrict__ dst, const int *__restrict__ perm,
+                                int G, int N, int Nc) {
+  const size_t total = (size_t)G * Nc;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i / Nc), j = (int)(i - (size_t)g * Nc);
+    dst[i] = j < N ? raw[(size_t)g * N + perm[j]] : 0;
+  }
+}
+
+__global__ void k_gene_consts(const int *__restrict__ counts, int G, int N, int Nc, double *lgam, double *nnz) {
+  __shared__ double red[kWarps * kRedMax];
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    double a = 0, b = 0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const int y = counts[(size_t)g * Nc + j];
+      if (y > 0) { a += lgamma((double)y + 1.0); b += 1.0; }
+    }
+    double r[2] = {a, b};
+    block_sum<2>(r, red);
+    if (threadIdx.x == 0) { lgam[g] = r[0]; nnz[g] = r[1]; }
+  }
+}
+
+// Stan order [R][D] -> internal [R][Di]
+__global__ void k_to_internal(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ imap,
+                              int R, int D, int Di, double pad_value) {
+  const size_t total = (size_t)R * Di;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / Di;
+    const int e = (int)(i - r * Di);
+    const int si = imap[e];
+    dst[i] = si >= 0 ? src[r * D + si] : pad_value;
+  }
+}
+// internal [R][Di] -> Stan order [R][D]
+__global__ void k_to_stan(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ imap,
+                          int R, int D, int Di) {
+  const size_t total = (size_t)R * Di;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / Di;
+    const int e = (int)(i - r * Di);
+    const int si = imap[e];
+    if (si >= 0) dst[r * D + si] = src[i];
+  }
+}
+
+// pooled-over-chains mean / std (ddof=0) of the streaming summaries, original spot order
+__global__ void k_summ_finalize(const double *__restrict__ summ, const ChainScalars *__restrict__ cs,
+                                const int *__restrict__ perm, int G, int nch, int N, int num_warmup,
+                                double *o0, double *o1, double *o2, double *o3, double *o4, double *o5) {
+  const size_t total = (size_t)G * N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i / N), j = (int)(i - (size_t)g * N);
+    const int jo = perm[j];
+    double *outs[6] = {o0, o1, o2, o3, o4, o5};
+    for (int q = 0; q < 3; ++q) {
+      double n = 0, mean = 0, M2 = 0;
+      for (int c = 0; c < nch; ++c) {
+        const int w = g * nch + c;
+        const double nc = (double)max(0, cs[w].iter - num_warmup);
+        if (nc <= 0) continue;
+        const double mc = summ[((size_t)w * 6 + 2 * q) * N + j], vc = summ[((size_t)w * 6 + 2 * q + 1) * N + j];
+        const double d = mc - mean, nt = n + nc;
+        mean += d * nc / nt;
+        M2 += vc + d * d * n * nc / nt;
+        n = nt;
+      }
+      if (outs[2 * q]) outs[2 * q][(size_t)g * N + jo] = mean;
+      if (outs[2 * q + 1]) outs[2 * q + 1][(size_t)g * N + jo] = n > 0 ? sqrt(M2 / n) : 0.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernels
+// ------------------------------------------------------------------------------------------------
+template <int KT>
+__device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, double *smem) {
+  ops.B = smem;
+  ops.adjB = smem + m.nbeta;
+  ops.red = smem + 2 * m.nbeta;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kBlock, 2)
+k_lpgrad(const __grid_constant__ DevModel m, const int *__restrict__ counts, const double *__restrict__ pm,
+         const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz, int G,
+         const double *__restrict__ theta_int, const int *__restrict__ gene_of, int Bn, double *lp_out,
+         double *grad_int, int jacobian) {
+  extern __shared__ double smem[];
+  DevOps<KT> ops(m);
+  bind_smem(ops, m, smem);
+  ops.jacobian = jacobian;
+  ops.minv = nullptr;
+  for (int b = blockIdx.x; b < Bn; b += gridDim.x) {
+    const int g = gene_of ? gene_of[b] : (b % G);
+    ops.gn.counts = counts + (size_t)g * m.Nc;
+    ops.gn.pm = pm ? pm + (size_t)g * m.K : nullptr;
+    ops.gn.ps = ps ? ps + (size_t)g * m.K : nullptr;
+    ops.gn.lgam = lgam[g];
+    ops.gn.nnz = nnz[g];
+    double V;
+    bool fin;
+    const double *q = theta_int + (size_t)b * m.Di;
+    ops.template eval<false>(q, nullptr, nullptr, const_cast<double *>(q), grad_int + (size_t)b * m.Di, nullptr,
+                             0.0, &V, nullptr, &fin);
+    if (threadIdx.x == 0) lp_out[b] = -V;
+    __syncthreads();
+  }
+}
+
+// grad_int of k_lpgrad holds g = -grad lp; flip the sign while converting to Stan order
+__global__ void k_negate(double *v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] = -v[i];
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kBlock, 2)
+k_leapfrog_fixed(const __grid_constant__ DevModel m, const int *__restrict__ counts, const double *__restrict__ pm,
+                 const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz,
+                 int G, double *q, double *p, double *g, const double *__restrict__ minv,
+                 const int *__restrict__ gene_of, int Bn, double eps, int n_steps, double *H_out) {
+  extern __shared__ double smem[];
+  DevOps<KT> ops(m);
+  bind_smem(ops, m, smem);
+  ops.jacobian = 1;
+  for (int b = blockIdx.x; b < Bn; b += gridDim.x) {
+    const int gi = gene_of ? gene_of[b] : (b % G);
+    ops.gn.counts = counts + (size_t)gi * m.Nc;
+    ops.gn.pm = pm ? pm + (size_t)gi * m.K : nullptr;
+    ops.gn.ps = ps ? ps + (size_t)gi * m.K : nullptr;
+    ops.gn.lgam = lgam[gi];
+    ops.gn.nnz = nnz[gi];
+    ops.minv = const_cast<double *>(minv) + (size_t)b * m.Di;
+    double *qb = q + (size_t)b * m.Di, *pb = p + (size_t)b * m.Di, *gb = g + (size_t)b * m.Di;
+    double V, K = 0.0;
+    bool fin;
+    ops.template eval<false>(qb, nullptr, nullptr, qb, gb, nullptr, 0.0, &V, nullptr, &fin);
+    for (int s = 0; s < n_steps; ++s) ops.template eval<true>(qb, gb, pb, qb, gb, pb, eps, &V, &K, nullptr);
+    if (n_steps == 0) {
+      double k = 0.0;
+      for (int e = threadIdx.x; e < m.Di; e += kBlock) k += ops.minv[e] * pb[e] * pb[e];
+      double r[1] = {k};
+      block_sum<1>(r, ops.red);
+      K = 0.5 * r[0];
+    }
+    if (threadIdx.x == 0) H_out[b] = V + K;
+    __syncthreads();
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kBlock, 2)
+k_nuts_advance(const __grid_constant__ DevModel m, const __grid_constant__ SamplerDev s, int n_iter) {
+  extern __shared__ double smem[];
+  __shared__ int s_work;
+  const size_t Di = m.Di;
+  double *ws = s.ws + (size_t)blockIdx.x * (size_t)(kPoolVecs + 6) * Di;
+  for (;;) {
+    if (threadIdx.x == 0) s_work = atomicAdd(s.queue, 1);
+    __syncthreads();
+    const int w = s_work;
+    __syncthreads();
+    if (w >= s.W) break;
+    const int g = w / s.num_chains, c = w - g * s.num_chains;
+    DevOps<KT> ops(m);
+    bind_smem(ops, m, smem);
+    ops.jacobian = 1;
+    ops.gn.counts = s.counts + (size_t)g * m.Nc;
+    ops.gn.pm = s.pm ? s.pm + (size_t)g * m.K : nullptr;
+    ops.gn.ps = s.ps ? s.ps + (size_t)g * m.K : nullptr;
+    ops.gn.lgam = s.lgam[g];
+    ops.gn.nnz = s.nnz[g];
+    ops.key = RngKey{s.cfg.seed, (uint32_t)c + 1u, s.gene_id0 + (uint32_t)g};
+    ops.pool = ws;
+    ops.zq[0] = ws + (size_t)kPoolVecs * Di;
+    ops.zg[0] = ops.zq[0] + Di;
+    ops.zq[1] = ops.zg[0] + Di;
+    ops.zg[1] = ops.zq[1] + Di;
+    ops.q_prop = ops.zg[1] + Di;
+    ops.q_samp = ops.q_prop + Di;
+    ops.q_cur = s.q_cur + (size_t)w * Di;
+    ops.minv = s.minv + (size_t)w * Di;
+    ops.wm = s.wm + (size_t)w * Di;
+    ops.wm2 = s.wm2 + (size_t)w * Di;
+    ops.sample_is_q0 = true;
+    const size_t ns = (size_t)s.cfg.num_samples;
+    ops.out_diag = s.diag ? s.diag + (size_t)w * ns * 7 : nullptr;
+    ops.out_small = s.small ? s.small + (size_t)w * ns * m.nsmall : nullptr;
+    ops.out_theta = s.theta ? s.theta + (size_t)w * ns * m.D : nullptr;
+    ops.out_summ = s.summ ? s.summ + (size_t)w * 6 * m.N : nullptr;
+    ChainScalars cs = s.cs[w];
+    Nuts<DevOps<KT>> nuts(ops, s.cfg, cs, ops.key);
+    nuts.advance(n_iter, s.have_init != 0);
+    __syncthreads();
+    if (threadIdx.x == 0) s.cs[w] = cs;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: model
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *csplotch_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t csplotch_abi_version(void) { return CSPLOTCH_ABI_VERSION; }
+extern "C" int32_t csplotch_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+extern "C" int32_t csplotch_set_device(int32_t device) {
+  CU_TRY(cudaSetDevice(device));
+  return CSPLOTCH_OK;
+}
+
+static int pick_kt(int K) {
+  if (K <= 1) return 1;
+  if (K <= 4) return 4;
+  if (K <= 8) return 8;
+  if (K <= 12) return 12;
+  if (K <= 16) return 16;
+  return 0;
+}
+
+extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch_model **out) {
+  if (!d || !out) return fail(CSPLOTCH_E_INVALID, "null argument");
+  *out = nullptr;
+  if (d->family < 0 || d->family > 2) return fail(CSPLOTCH_E_INVALID, "family must be 0,1,2");
+  if (d->family == CSPLOTCH_COMP_SPLOTCH && d->nb)
+    return fail(CSPLOTCH_E_UNSUPPORTED, "nb=1 (negative binomial likelihood) is not built yet");
+  if (d->N_tissues < 1 || !d->N_spots || !d->tissue_mapping || !d->D || !d->size_factors)
+    return fail(CSPLOTCH_E_INVALID, "missing N_spots / tissue_mapping / D / size_factors");
+  const int T = d->N_tissues, C = d->N_covariates;
+  const int K = d->family == CSPLOTCH_COMP_SPLOTCH ? d->N_celltypes : 1;
+  const int L1 = d->N_level_1, L2 = d->N_level_2, L3 = d->N_level_3, L = L1 + L2 + L3;
+  if (C < 1 || K < 1 || L1 < 1 || L2 < 0 || L3 < 0) return fail(CSPLOTCH_E_INVALID, "bad N_covariates / N_celltypes / N_level_k");
+  if (L3 > 0 && L2 == 0) return fail(CSPLOTCH_E_INVALID, "N_level_3 > 0 needs N_level_2 > 0");
+  if (d->family == CSPLOTCH_COMP_SPLOTCH && !d->E) return fail(CSPLOTCH_E_INVALID, "comp model needs E");
+  if ((L2 && !d->level_2_mapping) || (L3 && !d->level_3_mapping)) return fail(CSPLOTCH_E_INVALID, "missing level mapping");
+  long long Nll = 0;
+  for (int t = 0; t < T; ++t) {
+    if (d->N_spots[t] < 1) return fail(CSPLOTCH_E_INVALID, "N_spots must be >= 1");
+    Nll += d->N_spots[t];
+  }
+  if (Nll > (1ll << 30)) return fail(CSPLOTCH_E_INVALID, "too many spots");
+  const int N = (int)Nll;
+  const int car = d->car ? 1 : 0, zi = d->zi ? 1 : 0;
+  const int Lbot = L3 ? L3 : (L2 ? L2 : L1);
+  const int kt = pick_kt(K);
+  if (!kt) return fail(CSPLOTCH_E_UNSUPPORTED, "N_celltypes > 16 is not built yet");
+
+  auto *m = new csplotch_model();
+  cudaGetDevice(&m->device);
+  m->T = T;
+  m->kt = kt;
+  DevModel &dm = m->dm;
+  memset(&dm, 0, sizeof(dm));
+  dm.family = d->family; dm.N = N; dm.Npad = (N + 1) & ~1; dm.C = C; dm.K = K;
+  dm.L1 = L1; dm.L2 = L2; dm.L3 = L3; dm.L = L;
+  dm.bot0 = L3 ? L1 + L2 : (L2 ? L1 : 0);
+  dm.nbeta = L * C * K;
+  dm.zi = zi; dm.car = car;
+  int ns = 0;
+  dm.s_tau = car ? ns++ : -1;
+  dm.s_a = car ? ns++ : -1;
+  dm.s_sigma = ns++;
+  dm.s_s2 = L2 ? ns++ : -1;
+  dm.s_s3 = L3 ? ns++ : -1;
+  dm.s_theta = zi ? ns++ : -1;
+  dm.nscal = ns;
+  dm.nsmall = dm.nbeta + ns;
+  dm.nsmall_pad = (dm.nsmall + 1) & ~1;
+  dm.o_psi = 0;
+  dm.o_noise = car ? dm.Npad : 0;
+  dm.o_small = dm.o_noise + dm.Npad;
+  dm.Di = dm.o_small + dm.nsmall_pad;
+  dm.D = (car ? N : 0) + dm.nbeta + ns + N;
+  dm.Nc = (N + 3) & ~3;
+  m->n_outputs = dm.D + N + dm.nbeta;
+  m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax) * sizeof(double);
+  if (m->smem_bytes > 200 * 1024) {
+    delete m;
+    return fail(CSPLOTCH_E_UNSUPPORTED, "beta table (L*C*K) too large for shared memory");
+  }
+
+  // spot order: identity for now (the layout supports any permutation)
+  m->perm.resize(N);
+  for (int j = 0; j < N; ++j) m->perm[j] = j;
+  std::vector<int> inv(N);
+  for (int j = 0; j < N; ++j) inv[m->perm[j]] = j;
+
+  // Stan offsets (declaration order)
+  const int so_psi = 0, so_beta = car ? N : 0, so_scal = so_beta + dm.nbeta, so_noise = so_scal + ns;
+  m->imap.assign(dm.Di, -1);
+  for (int j = 0; j < N; ++j) {
+    if (car) m->imap[dm.o_psi + j] = so_psi + m->perm[j];
+    m->imap[dm.o_noise + j] = so_noise + m->perm[j];
+  }
+  for (int i = 0; i < L; ++i)
+    for (int j = 0; j < C; ++j)
+      for (int k = 0; k < K; ++k) {
+        const int internal = (i * C + j) * K + k;
+        const int stan = d->family == CSPLOTCH_COMP_SPLOTCH ? internal : i + L * j;
+        m->imap[dm.o_small + internal] = so_beta + stan;
+      }
+  for (int s = 0; s < ns; ++s) m->imap[dm.o_small + dm.nbeta + s] = so_scal + s;
+
+  // per-spot tables
+  std::vector<double> lsf(N);
+  std::vector<int> key(N);
+  {
+    std::vector<int> tissue_of(N);
+    int j = 0;
+    for (int t = 0; t < T; ++t) {
+      const int tm = d->tissue_mapping[t];
+      if (tm < 1 || tm > Lbot) { delete m; return fail(CSPLOTCH_E_INVALID, "tissue_mapping out of range"); }
+      for (int s = 0; s < d->N_spots[t]; ++s, ++j) tissue_of[j] = tm - 1;
+    }
+    for (int ji = 0; ji < N; ++ji) {
+      const int jo = m->perm[ji];
+      if (d->D[jo] < 1 || d->D[jo] > C) { delete m; return fail(CSPLOTCH_E_INVALID, "D out of range"); }
+      if (!(d->size_factors[jo] > 0)) { delete m; return fail(CSPLOTCH_E_INVALID, "size_factors must be > 0"); }
+      lsf[ji] = std::log(d->size_factors[jo]);
+      key[ji] = tissue_of[jo] * C + (d->D[jo] - 1);
+    }
+  }
+  std::vector<int> map2(L2), map3(L3);
+  for (int i = 0; i < L2; ++i) {
+    map2[i] = d->level_2_mapping[i] - 1;
+    if (map2[i] < 0 || map2[i] >= L1) { delete m; return fail(CSPLOTCH_E_INVALID, "level_2_mapping out of range"); }
+  }
+  for (int i = 0; i < L3; ++i) {
+    map3[i] = d->level_3_mapping[i] - 1;
+    if (map3[i] < 0 || map3[i] >= L2) { delete m; return fail(CSPLOTCH_E_INVALID, "level_3_mapping out of range"); }
+  }
+  std::vector<int> rowptr(N + 1, 0), col;
+  std::vector<double> eigu, eigm;
+  if (car) {
+    if (!d->eig_values) { delete m; return fail(CSPLOTCH_E_INVALID, "car=1 needs eig_values"); }
+    std::vector<std::vector<int>> adj(N);
+    if (d->U && d->V) {
+      for (int i = 0; i < N; ++i)
+        for (int e = d->U[i] - 1; e < d->U[i + 1] - 1; ++e) {
+          const int nb = d->V[e] - 1;
+          if (nb < 0 || nb >= N) { delete m; return fail(CSPLOTCH_E_INVALID, "V out of range"); }
+          adj[inv[i]].push_back(inv[nb]);
+        }
+    } else if (d->W_sparse) {
+      for (int e = 0; e < d->W_n; ++e) {
+        const int a = d->W_sparse[2 * e] - 1, b = d->W_sparse[2 * e + 1] - 1;
+        if (a < 0 || a >= N || b < 0 || b >= N) { delete m; return fail(CSPLOTCH_E_INVALID, "W_sparse out of range"); }
+        adj[inv[a]].push_back(inv[b]);
+        adj[inv[b]].push_back(inv[a]);
+      }
+    } else {
+      delete m;
+      return fail(CSPLOTCH_E_INVALID, "car=1 needs W_sparse or U,V");
+    }
+    for (int i = 0; i < N; ++i) {
+      std::sort(adj[i].begin(), adj[i].end());
+      rowptr[i + 1] = rowptr[i] + (int)adj[i].size();
+      col.insert(col.end(), adj[i].begin(), adj[i].end());
+      if (d->D_sparse && std::fabs(d->D_sparse[m->perm[i]] - (double)adj[i].size()) > 0.5) {
+        delete m;
+        return fail(CSPLOTCH_E_INVALID, "D_sparse does not match the adjacency");
+      }
+    }
+    // distinct eigenvalues with multiplicity (exact duplicates only; c3 has 24 identical arrays)
+    std::map<double, double> mult;
+    for (int i = 0; i < N; ++i) mult[d->eig_values[i]] += 1.0;
+    for (auto &kv : mult) { eigu.push_back(kv.first); eigm.push_back(kv.second); }
+    dm.n_eig = (int)eigu.size();
+  }
+  std::vector<double> E;
+  if (d->family == CSPLOTCH_COMP_SPLOTCH) {
+    E.resize((size_t)N * K);
+    for (int ji = 0; ji < N; ++ji)
+      for (int k = 0; k < K; ++k) E[(size_t)ji * K + k] = d->E[(size_t)m->perm[ji] * K + k];
+  }
+  bool ok = true;
+  double *p_lsf, *p_E, *p_eu, *p_em;
+  int *p_key, *p_rp, *p_col, *p_m2, *p_m3, *p_imap;
+  ok &= m->buf.upload(&p_lsf, lsf) == cudaSuccess;
+  ok &= m->buf.upload(&p_key, key) == cudaSuccess;
+  ok &= m->buf.upload(&p_rp, rowptr) == cudaSuccess;
+  ok &= m->buf.upload(&p_col, col) == cudaSuccess;
+  ok &= m->buf.upload(&p_E, E) == cudaSuccess;
+  ok &= m->buf.upload(&p_eu, eigu) == cudaSuccess;
+  ok &= m->buf.upload(&p_em, eigm) == cudaSuccess;
+  ok &= m->buf.upload(&p_m2, map2) == cudaSuccess;
+  ok &= m->buf.upload(&p_m3, map3) == cudaSuccess;
+  ok &= m->buf.upload(&p_imap, m->imap) == cudaSuccess;
+  if (!ok) {
+    std::string msg = cudaGetErrorString(cudaGetLastError());
+    delete m;
+    return fail(CSPLOTCH_E_CUDA, "model upload failed: " + msg);
+  }
+  dm.lsf = p_lsf; dm.key = p_key; dm.rowptr = p_rp; dm.col = p_col; dm.E = p_E; dm.eigu = p_eu; dm.eigm = p_em;
+  dm.map2 = p_m2; dm.map3 = p_m3; dm.imap = p_imap;
+  *out = m;
+  return CSPLOTCH_OK;
+}
+
+extern "C" void csplotch_model_destroy(csplotch_model *m) { delete m; }
+
+extern "C" int32_t csplotch_model_dims(const csplotch_model *m, csplotch_dims *o) {
+  if (!m || !o) return fail(CSPLOTCH_E_INVALID, "null argument");
+  o->N = m->dm.N; o->dim = m->dm.D; o->n_beta = m->dm.nbeta; o->n_scalar = m->dm.nscal;
+  o->n_small = m->dm.nsmall; o->n_outputs = m->n_outputs;
+  return CSPLOTCH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: batch
+// ------------------------------------------------------------------------------------------------
+static int batch_finish(csplotch_model *m, csplotch_batch *b, const int *counts_raw_dev, const double *pm,
+                        const double *ps, cudaStream_t st) {
+  const DevModel &dm = m->dm;
+  int *perm_dev = nullptr;
+  CU_TRY(b->buf.upload(&perm_dev, m->perm));
+  CU_TRY(b->buf.alloc(&b->counts, (size_t)b->G * dm.Nc));
+  CU_TRY(b->buf.alloc(&b->lgam, (size_t)b->G));
+  CU_TRY(b->buf.alloc(&b->nnz, (size_t)b->G));
+  k_repack_counts<<<1184, 256, 0, st>>>(counts_raw_dev, b->counts, perm_dev, b->G, dm.N, dm.Nc);
+  k_gene_consts<<<std::min(b->G, 1184), kBlock, 0, st>>>(b->counts, b->G, dm.N, dm.Nc, b->lgam, b->nnz);
+  CU_TRY(cudaGetLastError());
+  if (dm.family == CSPLOTCH_COMP_SPLOTCH) {
+    if (!pm || !ps) return fail(CSPLOTCH_E_INVALID, "comp model needs beta_prior_mean / beta_prior_std");
+    std::vector<double> hm(pm, pm + (size_t)b->G * dm.K), hs(ps, ps + (size_t)b->G * dm.K);
+    for (double v : hs)
+      if (!(v > 0)) return fail(CSPLOTCH_E_INVALID, "beta_prior_std must be > 0");
+    CU_TRY(b->buf.upload(&b->pm, hm));
+    CU_TRY(b->buf.upload(&b->ps, hs));
+  }
+  CU_TRY(cudaStreamSynchronize(st));
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_batch_create_dev(csplotch_model *m, const int32_t *counts_dev, const double *pm,
+                                             const double *ps, int32_t G, uint32_t gene_id0, void *stream,
+                                             csplotch_batch **out) {
+  if (!m || !counts_dev || !out || G < 1) return fail(CSPLOTCH_E_INVALID, "bad argument");
+  auto *b = new csplotch_batch();
+  b->m = m; b->G = G; b->gene_id0 = gene_id0;
+  int rc = batch_finish(m, b, counts_dev, pm, ps, (cudaStream_t)stream);
+  if (rc) { delete b; return rc; }
+  *out = b;
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_batch_create(csplotch_model *m, const int32_t *counts, const double *pm,
+                                         const double *ps, int32_t G, uint32_t gene_id0, csplotch_batch **out) {
+  if (!m || !counts || !out || G < 1) return fail(CSPLOTCH_E_INVALID, "bad argument");
+  const size_t n = (size_t)G * m->dm.N;
+  for (size_t i = 0; i < n; ++i)
+    if (counts[i] < 0) return fail(CSPLOTCH_E_INVALID, "counts must be >= 0");
+  int *raw = nullptr;
+  CU_TRY(cudaMalloc(&raw, n * sizeof(int)));
+  cudaError_t e = cudaMemcpy(raw, counts, n * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(raw); return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e)); }
+  int rc = csplotch_batch_create_dev(m, raw, pm, ps, G, gene_id0, nullptr, out);
+  cudaFree(raw);
+  return rc;
+}
+
+extern "C" void csplotch_batch_destroy(csplotch_batch *b) { delete b; }
+
+// ------------------------------------------------------------------------------------------------
+// host: launch helpers
+// ------------------------------------------------------------------------------------------------
+static int sm_count() {
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
+}
+
+#define DISPATCH_KT(kt, ...)                 \
+  switch (kt) {                               \
+    case 1: { constexpr int KT = 1; __VA_ARGS__; } break;   \
+    case 4: { constexpr int KT = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int KT = 8; __VA_ARGS__; } break;   \
+    case 12: { constexpr int KT = 12; __VA_ARGS__; } break; \
+    case 16: { constexpr int KT = 16; __VA_ARGS__; } break; \
+    default: return fail(CSPLOTCH_E_UNSUPPORTED, "unsupported N_celltypes"); \
+  }
+
+template <class Kern>
+static cudaError_t set_smem(Kern kern, size_t bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+extern "C" int32_t csplotch_log_prob_grad_dev(csplotch_batch *b, const double *theta_dev, const int32_t *gene_of_dev,
+                                              int32_t Bn, double *lp_dev, double *grad_dev, int32_t jacobian,
+                                              void *stream) {
+  if (!b || !theta_dev || !lp_dev || Bn < 1) return fail(CSPLOTCH_E_INVALID, "bad argument");
+  csplotch_model *m = b->m;
+  const DevModel &dm = m->dm;
+  cudaStream_t st = (cudaStream_t)stream;
+  double *th_int = nullptr, *g_int = nullptr;
+  CU_TRY(cudaMalloc(&th_int, (size_t)Bn * dm.Di * sizeof(double)));
+  if (cudaMalloc(&g_int, (size_t)Bn * dm.Di * sizeof(double)) != cudaSuccess) {
+    cudaFree(th_int);
+    return fail(CSPLOTCH_E_NOMEM, "out of device memory");
+  }
+  const int nb = sm_count() * 8;
+  k_to_internal<<<nb, 256, 0, st>>>(theta_dev, th_int, dm.imap, Bn, dm.D, dm.Di, 0.0);
+  const int grid = std::min(Bn, sm_count() * 2);
+  cudaError_t e = cudaSuccess;
+  DISPATCH_KT(m->kt, {
+    e = set_smem(k_lpgrad<KT>, m->smem_bytes);
+    if (e == cudaSuccess)
+      k_lpgrad<KT><<<grid, kBlock, m->smem_bytes, st>>>(dm, b->counts, b->pm, b->ps, b->lgam, b->nnz, b->G, th_int,
+                                                       gene_of_dev, Bn, lp_dev, g_int, jacobian);
+  });
+  if (e == cudaSuccess && grad_dev) {
+    k_negate<<<nb, 256, 0, st>>>(g_int, (size_t)Bn * dm.Di);
+    k_to_stan<<<nb, 256, 0, st>>>(g_int, grad_dev, dm.imap, Bn, dm.D, dm.Di);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(th_int);
+  cudaFree(g_int);
+  if (e != cudaSuccess) return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e));
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_log_prob_grad(csplotch_batch *b, const double *theta, const int32_t *gene_of, int32_t Bn,
+                                          double *lp, double *grad, int32_t jacobian) {
+  if (!b || !theta || !lp || Bn < 1) return fail(CSPLOTCH_E_INVALID, "bad argument");
+  const DevModel &dm = b->m->dm;
+  if (gene_of)
+    for (int i = 0; i < Bn; ++i)
+      if (gene_of[i] < 0 || gene_of[i] >= b->G) return fail(CSPLOTCH_E_INVALID, "gene_of out of range");
+  DevBuf tmp;
+  double *th = nullptr, *lpd = nullptr, *gd = nullptr;
+  int *go = nullptr;
+  CU_TRY(tmp.alloc(&th, (size_t)Bn * dm.D));
+  CU_TRY(tmp.alloc(&lpd, (size_t)Bn));
+  if (grad) CU_TRY(tmp.alloc(&gd, (size_t)Bn * dm.D));
+  if (gene_of) {
+    CU_TRY(tmp.alloc(&go, (size_t)Bn));
+    CU_TRY(cudaMemcpy(go, gene_of, (size_t)Bn * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  CU_TRY(cudaMemcpy(th, theta, (size_t)Bn * dm.D * sizeof(double), cudaMemcpyHostToDevice));
+  int rc = csplotch_log_prob_grad_dev(b, th, go, Bn, lpd, gd, jacobian, nullptr);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpy(lp, lpd, (size_t)Bn * sizeof(double), cudaMemcpyDeviceToHost));
+  if (grad) CU_TRY(cudaMemcpy(grad, gd, (size_t)Bn * dm.D * sizeof(double), cudaMemcpyDeviceToHost));
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_leapfrog_fixed(csplotch_batch *b, const double *theta0, const double *p0,
+                                           const double *inv_metric, const int32_t *gene_of, int32_t Bn, double eps,
+                                           int32_t n_steps, double *theta_out, double *p_out, double *H_out) {
+  if (!b || !theta0 || !p0 || !inv_metric || Bn < 1 || n_steps < 0) return fail(CSPLOTCH_E_INVALID, "bad argument");
+  csplotch_model *m = b->m;
+  const DevModel &dm = m->dm;
+  DevBuf tmp;
+  double *stan = nullptr, *q = nullptr, *p = nullptr, *g = nullptr, *mi = nullptr, *H = nullptr;
+  int *go = nullptr;
+  const size_t nS = (size_t)Bn * dm.D, nI = (size_t)Bn * dm.Di;
+  CU_TRY(tmp.alloc(&stan, nS));
+  CU_TRY(tmp.alloc(&q, nI));
+  CU_TRY(tmp.alloc(&p, nI));
+  CU_TRY(tmp.alloc(&g, nI));
+  CU_TRY(tmp.alloc(&mi, nI));
+  CU_TRY(tmp.alloc(&H, (size_t)Bn));
+  if (gene_of) {
+    CU_TRY(tmp.alloc(&go, (size_t)Bn));
+    CU_TRY(cudaMemcpy(go, gene_of, (size_t)Bn * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  const int nb = sm_count() * 8;
+  CU_TRY(cudaMemcpy(stan, theta0, nS * sizeof(double), cudaMemcpyHostToDevice));
+  k_to_internal<<<nb, 256>>>(stan, q, dm.imap, Bn, dm.D, dm.Di, 0.0);
+  CU_TRY(cudaMemcpy(stan, p0, nS * sizeof(double), cudaMemcpyHostToDevice));
+  k_to_internal<<<nb, 256>>>(stan, p, dm.imap, Bn, dm.D, dm.Di, 0.0);
+  CU_TRY(cudaMemcpy(stan, inv_metric, nS * sizeof(double), cudaMemcpyHostToDevice));
+  k_to_internal<<<nb, 256>>>(stan, mi, dm.imap, Bn, dm.D, dm.Di, 1.0);
+  const int grid = std::min(Bn, sm_count() * 2);
+  cudaError_t e = cudaSuccess;
+  DISPATCH_KT(m->kt, {
+    e = set_smem(k_leapfrog_fixed<KT>, m->smem_bytes);
+    if (e == cudaSuccess)
+      k_leapfrog_fixed<KT><<<grid, kBlock, m->smem_bytes>>>(dm, b->counts, b->pm, b->ps, b->lgam, b->nnz, b->G, q, p, g,
+                                                           mi, go, Bn, eps, n_steps, H);
+  });
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e));
+  if (theta_out) {
+    k_to_stan<<<nb, 256>>>(q, stan, dm.imap, Bn, dm.D, dm.Di);
+    CU_TRY(cudaMemcpy(theta_out, stan, nS * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (p_out) {
+    k_to_stan<<<nb, 256>>>(p, stan, dm.imap, Bn, dm.D, dm.Di);
+    CU_TRY(cudaMemcpy(p_out, stan, nS * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (H_out) CU_TRY(cudaMemcpy(H_out, H, (size_t)Bn * sizeof(double), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaDeviceSynchronize());
+  return CSPLOTCH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: sampler
+// ------------------------------------------------------------------------------------------------
+extern "C" void csplotch_nuts_cfg_default(csplotch_nuts_cfg *c) {
+  if (!c) return;
+  c->num_warmup = 1000; c->num_samples = 1000; c->num_chains = 4; c->max_depth = 10;
+  c->delta = 0.8; c->gamma = 0.05; c->kappa = 0.75; c->t0 = 10;
+  c->init_buffer = 75; c->term_buffer = 50; c->window = 25;
+  c->init_radius = 2; c->stepsize = 1; c->seed = 0; c->keep_draws = 0;
+}
+
+extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nuts_cfg *cfg, csplotch_sampler **out) {
+  if (!b || !cfg || !out) return fail(CSPLOTCH_E_INVALID, "null argument");
+  if (cfg->num_chains < 1 || cfg->num_warmup < 0 || cfg->num_samples < 0) return fail(CSPLOTCH_E_INVALID, "bad chain / iteration counts");
+  if (cfg->max_depth < 1 || cfg->max_depth > kMaxDepth) return fail(CSPLOTCH_E_INVALID, "max_depth must be in 1..12");
+  csplotch_model *m = b->m;
+  const DevModel &dm = m->dm;
+  auto *s = new csplotch_sampler();
+  s->b = b; s->cfg = *cfg;
+  SamplerDev &sd = s->sd;
+  memset(&sd, 0, sizeof(sd));
+  const int W = b->G * cfg->num_chains;
+  sd.W = W; sd.num_chains = cfg->num_chains; sd.gene_id0 = b->gene_id0;
+  sd.cfg = NutsConfig{cfg->num_warmup, cfg->num_samples, cfg->max_depth, cfg->delta, cfg->gamma, cfg->kappa, cfg->t0,
+                      cfg->init_buffer, cfg->term_buffer, cfg->window, cfg->init_radius, cfg->stepsize, cfg->seed};
+  sd.counts = b->counts; sd.pm = b->pm; sd.ps = b->ps; sd.lgam = b->lgam; sd.nnz = b->nnz;
+  s->grid = std::min(W, sm_count() * 2);
+  sd.n_slots = s->grid;
+  const size_t Di = dm.Di, ns = (size_t)cfg->num_samples;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](auto **p, size_t n) { if (e == cudaSuccess) e = s->buf.alloc(p, n); };
+  A(&sd.cs, (size_t)W);
+  A(&sd.q_cur, (size_t)W * Di);
+  A(&sd.minv, (size_t)W * Di);
+  A(&sd.wm, (size_t)W * Di);
+  A(&sd.wm2, (size_t)W * Di);
+  A(&sd.ws, (size_t)sd.n_slots * (kPoolVecs + 6) * Di);
+  A(&sd.diag, (size_t)W * ns * 7);
+  A(&sd.small, (size_t)W * ns * dm.nsmall);
+  A(&sd.summ, (size_t)W * 6 * dm.N);
+  if (cfg->keep_draws) A(&sd.theta, (size_t)W * ns * dm.D);
+  A(&sd.queue, 1);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(e == cudaErrorMemoryAllocation ? CSPLOTCH_E_NOMEM : CSPLOTCH_E_CUDA,
+                std::string("sampler allocation failed: ") + cudaGetErrorString(e));
+  }
+  CU_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreate(&s->ev0));
+  CU_TRY(cudaEventCreate(&s->ev1));
+  CU_TRY(cudaMemsetAsync(sd.cs, 0, (size_t)W * sizeof(ChainScalars), s->stream));
+  CU_TRY(cudaMemsetAsync(sd.q_cur, 0, (size_t)W * Di * sizeof(double), s->stream));
+  CU_TRY(cudaMemsetAsync(sd.ws, 0, (size_t)sd.n_slots * (kPoolVecs + 6) * Di * sizeof(double), s->stream));
+  CU_TRY(cudaMemsetAsync(sd.summ, 0, (size_t)W * 6 * dm.N * sizeof(double), s->stream));
+  CU_TRY(cudaMemsetAsync(sd.diag, 0, (size_t)W * ns * 7 * sizeof(double), s->stream));
+  CU_TRY(cudaMemsetAsync(sd.small, 0, (size_t)W * ns * dm.nsmall * sizeof(double), s->stream));
+  CU_TRY(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return CSPLOTCH_OK;
+}
+
+extern "C" void csplotch_sampler_destroy(csplotch_sampler *s) { delete s; }
+
+extern "C" int32_t csplotch_sampler_init(csplotch_sampler *s, const double *theta_init) {
+  if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
+  const DevModel &dm = s->b->m->dm;
+  if (theta_init) {
+    DevBuf tmp;
+    double *stan = nullptr;
+    const size_t n = (size_t)s->sd.W * dm.D;
+    CU_TRY(tmp.alloc(&stan, n));
+    CU_TRY(cudaMemcpy(stan, theta_init, n * sizeof(double), cudaMemcpyHostToDevice));
+    k_to_internal<<<sm_count() * 8, 256, 0, s->stream>>>(stan, s->sd.q_cur, dm.imap, s->sd.W, dm.D, dm.Di, 0.0);
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    s->sd.have_init = 1;
+  }
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_advance(csplotch_sampler *s, int32_t n_iter, int32_t sync) {
+  if (!s || n_iter < 0) return fail(CSPLOTCH_E_INVALID, "bad argument");
+  csplotch_model *m = s->b->m;
+  CU_TRY(cudaMemsetAsync(s->sd.queue, 0, sizeof(int), s->stream));
+  CU_TRY(cudaEventRecord(s->ev0, s->stream));
+  cudaError_t e = cudaSuccess;
+  DISPATCH_KT(m->kt, {
+    e = set_smem(k_nuts_advance<KT>, m->smem_bytes);
+    if (e == cudaSuccess) k_nuts_advance<KT><<<s->grid, kBlock, m->smem_bytes, s->stream>>>(m->dm, s->sd, n_iter);
+  });
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e));
+  CU_TRY(cudaEventRecord(s->ev1, s->stream));
+  s->timed = true;
+  s->launches += 1;
+  if (sync) CU_TRY(cudaStreamSynchronize(s->stream));
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_sync(csplotch_sampler *s) {
+  if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
+  CU_TRY(cudaStreamSynchronize(s->stream));
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_last_ms(csplotch_sampler *s, float *ms) {
+  if (!s || !ms || !s->timed) return fail(CSPLOTCH_E_INVALID, "no advance has been timed");
+  CU_TRY(cudaEventSynchronize(s->ev1));
+  CU_TRY(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+  return CSPLOTCH_OK;
+}
+
+static int fetch_cs(csplotch_sampler *s, std::vector<ChainScalars> &h) {
+  h.resize(s->sd.W);
+  CU_TRY(cudaStreamSynchronize(s->stream));
+  CU_TRY(cudaMemcpy(h.data(), s->sd.cs, h.size() * sizeof(ChainScalars), cudaMemcpyDeviceToHost));
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_counters(csplotch_sampler *s, int64_t *n_leapfrog, int64_t *n_grad,
+                                             int64_t *n_divergent, int64_t *n_launches) {
+  if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
+  std::vector<ChainScalars> h;
+  int rc = fetch_cs(s, h);
+  if (rc) return rc;
+  int64_t a = 0, b = 0, c = 0;
+  for (auto &x : h) { a += x.n_leapfrog_total; b += x.n_grad_total; c += x.n_divergent; }
+  if (n_leapfrog) *n_leapfrog = a;
+  if (n_grad) *n_grad = b;
+  if (n_divergent) *n_divergent = c;
+  if (n_launches) *n_launches = s->launches;
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_status(csplotch_sampler *s, int32_t *status, int32_t *iters_done) {
+  if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
+  std::vector<ChainScalars> h;
+  int rc = fetch_cs(s, h);
+  if (rc) return rc;
+  for (size_t i = 0; i < h.size(); ++i) {
+    if (status) status[i] = h[i].status;
+    if (iters_done) iters_done[i] = h[i].iter;
+  }
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_get_draws(csplotch_sampler *s, double *diag, double *small, int32_t *n_draws) {
+  if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
+  const DevModel &dm = s->b->m->dm;
+  const size_t ns = (size_t)s->cfg.num_samples, W = (size_t)s->sd.W;
+  CU_TRY(cudaStreamSynchronize(s->stream));
+  if (diag) CU_TRY(cudaMemcpy(diag, s->sd.diag, W * ns * 7 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (small) CU_TRY(cudaMemcpy(small, s->sd.small, W * ns * dm.nsmall * sizeof(double), cudaMemcpyDeviceToHost));
+  if (n_draws) {
+    std::vector<ChainScalars> h;
+    int rc = fetch_cs(s, h);
+    if (rc) return rc;
+    for (size_t i = 0; i < W; ++i) n_draws[i] = std::max(0, h[i].iter - s->cfg.num_warmup);
+  }
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_get_theta_draws(csplotch_sampler *s, double *theta) {
+  if (!s || !theta) return fail(CSPLOTCH_E_INVALID, "null argument");
+  if (!s->sd.theta) return fail(CSPLOTCH_E_INVALID, "sampler was created without keep_draws");
+  const DevModel &dm = s->b->m->dm;
+  CU_TRY(cudaStreamSynchronize(s->stream));
+  CU_TRY(cudaMemcpy(theta, s->sd.theta, (size_t)s->sd.W * s->cfg.num_samples * dm.D * sizeof(double), cudaMemcpyDeviceToHost));
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_get_state(csplotch_sampler *s, double *theta, double *stepsize, double *inv_metric) {
+  if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
+  const DevModel &dm = s->b->m->dm;
+  const size_t W = (size_t)s->sd.W;
+  CU_TRY(cudaStreamSynchronize(s->stream));
+  DevBuf tmp;
+  double *stan = nullptr;
+  CU_TRY(tmp.alloc(&stan, W * dm.D));
+  const int nb = sm_count() * 8;
+  if (theta) {
+    k_to_stan<<<nb, 256, 0, s->stream>>>(s->sd.q_cur, stan, dm.imap, (int)W, dm.D, dm.Di);
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    CU_TRY(cudaMemcpy(theta, stan, W * dm.D * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (inv_metric) {
+    k_to_stan<<<nb, 256, 0, s->stream>>>(s->sd.minv, stan, dm.imap, (int)W, dm.D, dm.Di);
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    CU_TRY(cudaMemcpy(inv_metric, stan, W * dm.D * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (stepsize) {
+    std::vector<ChainScalars> h;
+    int rc = fetch_cs(s, h);
+    if (rc) return rc;
+    for (size_t i = 0; i < W; ++i) stepsize[i] = h[i].eps;
+  }
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_get_spot_summaries(csplotch_sampler *s, double *ll_mean, double *ll_std,
+                                                       double *la_mean, double *la_std, double *psi_mean,
+                                                       double *psi_std) {
+  if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
+  const DevModel &dm = s->b->m->dm;
+  const int G = s->b->G;
+  const size_t n = (size_t)G * dm.N;
+  double *host[6] = {ll_mean, ll_std, la_mean, la_std, psi_mean, psi_std};
+  double *dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  DevBuf tmp;
+  int *perm_dev = nullptr;
+  CU_TRY(tmp.upload(&perm_dev, s->b->m->perm));
+  for (int i = 0; i < 6; ++i)
+    if (host[i]) CU_TRY(tmp.alloc(&dev[i], n));
+  k_summ_finalize<<<sm_count() * 8, 256, 0, s->stream>>>(s->sd.summ, s->sd.cs, perm_dev, G, s->cfg.num_chains, dm.N,
+                                                        s->cfg.num_warmup, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5]);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < 6; ++i)
+    if (host[i]) CU_TRY(cudaMemcpy(host[i], dev[i], n * sizeof(double), cudaMemcpyDeviceToHost));
+  return CSPLOTCH_OK;
+}
+
+// write_array is host-side glue over small per-draw blocks; the heavy part (log_lambda) is
+// evaluated on the device through the same load_small + spot loop as the sampler.
+template <int KT>
+__global__ void __launch_bounds__(kBlock, 2)
+k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm, const double *__restrict__ ps, int G,
+              const double *__restrict__ theta_int, const int *__restrict__ gene_of, const int *__restrict__ perm,
+              int Bn, double *out, int n_out) {
+  extern __shared__ double smem[];
+  DevOps<KT> ops(m);
+  bind_smem(ops, m, smem);
+  ops.jacobian = 0;
+  const int CK = m.C * m.K;
+  for (int b = blockIdx.x; b < Bn; b += gridDim.x) {
+    const int g = gene_of ? gene_of[b] : (b % G);
+    ops.gn.pm = pm ? pm + (size_t)g * m.K : nullptr;
+    ops.gn.ps = ps ? ps + (size_t)g * m.K : nullptr;
+    const double *q = theta_int + (size_t)b * m.Di;
+    double *o = out + (size_t)b * n_out;
+    Scalars sc;
+    ops.load_small(q, sc);
+    // constrained parameters in declaration order (Stan index space)
+    const int so_beta = m.car ? m.N : 0, so_scal = so_beta + m.nbeta;
+    for (int e = threadIdx.x; e < m.Di; e += kBlock) {
+      const int si = m.imap[e];
+      if (si < 0) continue;
+      double v = q[e];
+      if (si >= so_scal && si < so_scal + m.nscal) {
+        const int sidx = si - so_scal;
+        if (sidx == m.s_tau) v = sc.tau;
+        else if (sidx == m.s_a) v = sc.a;
+        else if (sidx == m.s_sigma) v = sc.sigma;
+        else if (sidx == m.s_s2) v = sc.s2;
+        else if (sidx == m.s_s3) v = sc.s3;
+        else if (sidx == m.s_theta) v = sc.theta;
+      }
+      // beta_raw is written column-major over (i,j,k): first index fastest
+      int oi = si;
+      if (si >= so_beta && si < so_scal) {
+        const int internal = e - m.o_small;
+        const int i = internal / CK, rem = internal - i * CK, j = rem / m.K, k = rem - j * m.K;
+        oi = so_beta + i + m.L * (j + m.C * k);
+      }
+      o[oi] = v;
+    }
+    // transformed parameters: log_lambda (original spot order), beta_level_1..3 (column-major)
+    double *oll = o + m.D;
+    const double sig03 = 0.3 * sc.sigma;
+    for (int j = threadIdx.x; j < m.N; j += kBlock) {
+      const double *bj = ops.B + (m.bot0 * m.C) * m.K + m.key[j] * m.K;
+      double ll = 0.0;
+      if (KT == 1) ll = bj[0];
+      else {
+        const double *Ej = m.E + (size_t)j * m.K;
+        for (int k = 0; k < m.K; ++k) ll += bj[k] * Ej[k];
+      }
+      if (m.car) ll += q[m.o_psi + j];
+      ll += sig03 * q[m.o_noise + j];
+      oll[perm[j]] = ll;
+    }
+    double *ob = oll + m.N;
+    for (int idx = threadIdx.x; idx < m.nbeta; idx += kBlock) {
+      const int i = idx / CK, rem = idx - i * CK, j = rem / m.K, k = rem - j * m.K;
+      int lev0, nr, off;
+      if (i < m.L1) { lev0 = 0; nr = m.L1; off = 0; }
+      else if (i < m.L1 + m.L2) { lev0 = m.L1; nr = m.L2; off = m.L1 * CK; }
+      else { lev0 = m.L1 + m.L2; nr = m.L3; off = (m.L1 + m.L2) * CK; }
+      ob[off + (i - lev0) + nr * (j + m.C * k)] = ops.B[idx];
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int32_t csplotch_write_array(csplotch_batch *b, const double *theta, const int32_t *gene_of, int32_t Bn,
+                                        double *out) {
+  if (!b || !theta || !out || Bn < 1) return fail(CSPLOTCH_E_INVALID, "bad argument");
+  csplotch_model *m = b->m;
+  const DevModel &dm = m->dm;
+  DevBuf tmp;
+  double *stan = nullptr, *q = nullptr, *o = nullptr;
+  int *go = nullptr, *perm_dev = nullptr;
+  CU_TRY(tmp.alloc(&stan, (size_t)Bn * dm.D));
+  CU_TRY(tmp.alloc(&q, (size_t)Bn * dm.Di));
+  CU_TRY(tmp.alloc(&o, (size_t)Bn * m->n_outputs));
+  CU_TRY(tmp.upload(&perm_dev, m->perm));
+  if (gene_of) {
+    CU_TRY(tmp.alloc(&go, (size_t)Bn));
+    CU_TRY(cudaMemcpy(go, gene_of, (size_t)Bn * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  CU_TRY(cudaMemcpy(stan, theta, (size_t)Bn * dm.D * sizeof(double), cudaMemcpyHostToDevice));
+  k_to_internal<<<sm_count() * 8, 256>>>(stan, q, dm.imap, Bn, dm.D, dm.Di, 0.0);
+  cudaError_t e = cudaSuccess;
+  DISPATCH_KT(m->kt, {
+    e = set_smem(k_write_array<KT>, m->smem_bytes);
+    if (e == cudaSuccess)
+      k_write_array<KT><<<std::min(Bn, sm_count() * 2), kBlock, m->smem_bytes>>>(dm, b->pm, b->ps, b->G, q, go, perm_dev,
+                                                                                Bn, o, m->n_outputs);
+  });
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e));
+  CU_TRY(cudaMemcpy(out, o, (size_t)Bn * m->n_outputs * sizeof(double), cudaMemcpyDeviceToHost));
+  return CSPLOTCH_OK;
+}

@@ -1,0 +1,609 @@
+// device_ops.cuh — CTA-collective vector operations of one gene-chain (sm_100a).
+//
+// One CTA owns one gene-chain.  Every function here is called by ALL threads of the CTA with
+// identical (uniform) scalar arguments and returns identical scalars to all of them (block
+// reductions are broadcast through shared memory in a fixed order), so the control flow in
+// nuts_core.h stays CTA-uniform.
+//
+// The fused log-density + gradient restates (reference files under
+// /root/reference/stan/):
+//   transformed parameters{}  splotch_stan_model.stan:100-181, comp_…:110-215  -> load_small()
+//   log_lambda + likelihood   splotch_stan_model.stan:135-180,209-222, comp_…:155-206,267-280,
+//                             _csr.stan:254-271                                  -> spot loop
+//   sparse_car_lpdf           splotch_stan_model.stan:4-17, _csr.stan:4-25       -> CSR gather + eig loop
+//   priors                    splotch_stan_model.stan:184-207                    -> finish()
+// Internal vector layout (all vectors of a chain, HBM):  [ psi(Npad) | noise(Npad) | small ]
+// small = beta_raw[(i*C+j)*K+k] | tau | a | sigma | sigma_level_2 | sigma_level_3 | theta.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nuts_core.h"
+
+namespace csp {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+constexpr int kRedMax = 12;  // doubles per block reduction
+
+struct DevModel {
+  int family, N, Npad, C, K, L1, L2, L3, L, bot0, nbeta, nscal, nsmall, nsmall_pad;
+  int zi, car;
+  int D;   // Stan dimension
+  int Di;  // internal dimension (padded)
+  int o_psi, o_noise, o_small;
+  int s_tau, s_a, s_sigma, s_s2, s_s3, s_theta;  // index inside the scalar part, -1 if absent
+  int n_eig;
+  int Nc;  // row stride of the counts matrix (int32 elements)
+  const double *lsf;     // [N] log(size_factors)
+  const int *key;        // [N] bottom-level bin: (tissue_mapping[t]-1)*C + D_j-1
+  const int *rowptr;     // [N+1] CSR of the symmetric adjacency (internal spot ids)
+  const int *col;        // [2 W_n]
+  const double *E;       // [N][K]
+  const double *eigu;    // [n_eig] distinct eigenvalues
+  const double *eigm;    // [n_eig] multiplicities
+  const int *map2;       // [L2] 0-based level-1 row of each level-2 row
+  const int *map3;       // [L3] 0-based level-2 row of each level-3 row
+  const int *imap;       // [Di] internal index -> Stan index (-1 = padding)
+};
+
+struct GeneDev {
+  const int *counts;   // [N] internal spot order
+  const double *pm;    // [K] beta_prior_mean (comp) or nullptr
+  const double *ps;    // [K] beta_prior_std
+  double lgam;         // sum_{y>0} lgamma(y+1)   (kept only under `target +=`, i.e. zi=1)
+  double nnz;          // #{y>0}
+};
+
+struct Scalars {
+  double tau, a, sigma, s2, s3, theta;
+  double jac;  // sum of log-Jacobians
+};
+
+__device__ __forceinline__ double inv_logit_d(double u) {
+  if (u < 0) {
+    const double e = exp(u);
+    return e / (1.0 + e);
+  }
+  return 1.0 / (1.0 + exp(-u));
+}
+__device__ __forceinline__ double log_inv_logit_d(double u) { return u < 0 ? u - log1p(exp(u)) : -log1p(exp(-u)); }
+__device__ __forceinline__ double log1m_inv_logit_d(double u) { return u > 0 ? -u - log1p(exp(-u)) : -log1p(exp(u)); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of NV values; result identical in every thread
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *red) {
+  static_assert(NV <= kRedMax, "raise kRedMax");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double s = warp_sum(v[i]);
+    if (lane == 0) red[warp * kRedMax + i] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w * kRedMax + i];
+    v[i] = s;
+  }
+  __syncthreads();
+}
+
+template <int KT>
+struct DevOps {
+  const DevModel &m;
+  GeneDev gn;
+  RngKey key;
+  int jacobian;
+  // shared memory: B[nbeta] | adjB[nbeta] | red[kWarps*kRedMax]
+  double *B, *adjB, *red;
+  // HBM vectors of this CTA slot / chain
+  double *pool;         // kPoolVecs x Di
+  double *zq[2], *zg[2];
+  double *q_prop, *q_samp;
+  double *q_cur, *minv, *wm, *wm2;
+  bool sample_is_q0;
+  // outputs of this chain (may be null)
+  double *out_diag;   // [num_samples][7]
+  double *out_small;  // [num_samples][nsmall]
+  double *out_theta;  // [num_samples][D] Stan order
+  double *out_summ;   // [6][N]: mean,M2 of log_lambda | mean,M2 of lambda | mean,M2 of psi
+  long long launches_dummy;
+
+  __device__ __forceinline__ DevOps(const DevModel &mm) : m(mm) {}
+
+  __device__ __forceinline__ double *vec(int id) const { return pool + (size_t)id * m.Di; }
+
+  // ---- constrained scalars + beta levels into shared memory --------------------------------
+  __device__ __forceinline__ void load_small(const double *q, Scalars &sc) {
+    const double *sb = q + m.o_small;
+    const double *ss = sb + m.nbeta;
+    sc.tau = sc.a = sc.s2 = sc.s3 = sc.theta = 0.0;
+    double jac = 0.0;
+    if (m.car) {
+      double u = ss[m.s_tau];
+      sc.tau = exp(u);
+      jac += u;
+      u = ss[m.s_a];
+      sc.a = inv_logit_d(u);
+      jac += log_inv_logit_d(u) + log1m_inv_logit_d(u);
+    }
+    {
+      const double u = ss[m.s_sigma];
+      sc.sigma = exp(u);
+      jac += u;
+    }
+    if (m.L2) { const double u = ss[m.s_s2]; sc.s2 = exp(u); jac += u; }
+    if (m.L3) { const double u = ss[m.s_s3]; sc.s3 = exp(u); jac += u; }
+    if (m.zi) {
+      const double u = ss[m.s_theta];
+      sc.theta = inv_logit_d(u);
+      jac += log_inv_logit_d(u) + log1m_inv_logit_d(u);
+    }
+    sc.jac = jacobian ? jac : 0.0;
+    const int CK = m.C * m.K;
+    for (int idx = threadIdx.x; idx < m.L1 * CK; idx += kBlock) {
+      const double r = sb[idx];
+      B[idx] = (m.family == 1) ? r * gn.ps[idx % m.K] + gn.pm[idx % m.K] : 2.0 * r;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < m.L2 * CK; idx += kBlock) {
+      const int i = idx / CK, rem = idx - i * CK;
+      B[(m.L1 + i) * CK + rem] = B[m.map2[i] * CK + rem] + sc.s2 * sb[(m.L1 + i) * CK + rem];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < m.L3 * CK; idx += kBlock) {
+      const int i = idx / CK, rem = idx - i * CK;
+      B[(m.L1 + m.L2 + i) * CK + rem] =
+          B[(m.L1 + m.map3[i]) * CK + rem] + sc.s3 * sb[(m.L1 + m.L2 + i) * CK + rem];
+    }
+    __syncthreads();
+  }
+
+  // warp-collective flush of the per-lane bottom-level bins into adjB (shared)
+  __device__ __forceinline__ void flush_bins(double (&acc)[KT], int cur_key) {
+    const int lane = threadIdx.x & 31;
+    unsigned remaining = __ballot_sync(0xffffffffu, cur_key >= 0);
+    while (remaining) {
+      const int leader = __ffs(remaining) - 1;
+      const int k0 = __shfl_sync(0xffffffffu, cur_key, leader);
+      const bool mine = (cur_key == k0);
+      const unsigned same = __ballot_sync(0xffffffffu, mine);
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        if (k < m.K) {
+          const double s = warp_sum(mine ? acc[k] : 0.0);
+          if (lane == leader) atomicAdd(&adjB[(m.bot0 * m.C) * m.K + k0 * m.K + k], s);
+        }
+      }
+      remaining &= ~same;
+    }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) acc[k] = 0.0;
+  }
+
+  // ---- fused [half-kick, drift,] log-density + gradient [, half-kick] ------------------------
+  // LEAP: (sq,sg,sp) --eps--> (dq,dg,dp).  !LEAP: dq := sq (if different), dg := -grad lp(sq).
+  // g vectors hold the gradient of the potential V = -lp, like Stan's ps_point::g.
+  template <bool LEAP>
+  __device__ void eval(const double *sq, const double *sg, const double *sp, double *dq, double *dg,
+                       double *dp, double eps, double *V_out, double *K_out, bool *finite_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Di = m.Di;
+    // phase A: half-kick + drift for every element (the spot loop below gathers psi of
+    // neighbours, so all of psi must have moved before any gradient is taken)
+    if (LEAP) {
+      for (int e = 2 * tid; e < Di; e += 2 * kBlock) {
+        const double2 q = *reinterpret_cast<const double2 *>(sq + e);
+        const double2 g = *reinterpret_cast<const double2 *>(sg + e);
+        const double2 p = *reinterpret_cast<const double2 *>(sp + e);
+        const double2 mi = *reinterpret_cast<const double2 *>(minv + e);
+        double2 ph, qn;
+        ph.x = p.x - 0.5 * eps * g.x;
+        ph.y = p.y - 0.5 * eps * g.y;
+        qn.x = q.x + eps * mi.x * ph.x;
+        qn.y = q.y + eps * mi.y * ph.y;
+        *reinterpret_cast<double2 *>(dq + e) = qn;
+        *reinterpret_cast<double2 *>(dp + e) = ph;
+      }
+    } else if (dq != sq) {
+      for (int e = 2 * tid; e < Di; e += 2 * kBlock)
+        *reinterpret_cast<double2 *>(dq + e) = *reinterpret_cast<const double2 *>(sq + e);
+    }
+    __syncthreads();
+
+    Scalars sc;
+    load_small(dq, sc);
+    for (int idx = tid; idx < m.nbeta; idx += kBlock) adjB[idx] = 0.0;
+    __syncthreads();
+
+    const double heads = m.zi ? log(sc.theta) : 0.0;
+    const double tails = m.zi ? log1p(-sc.theta) : 0.0;
+    const double sig03 = 0.3 * sc.sigma;
+    const double *psi = dq + m.o_psi;
+    const double *noi = dq + m.o_noise;
+    double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0;
+    double acc[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) acc[k] = 0.0;
+    int cur_key = -1;
+
+    // each warp owns a contiguous chunk of spots, 32 consecutive spots per trip
+    const int chunk = (((m.N + kWarps - 1) / kWarps) + 31) & ~31;
+    const int j_end = min(m.N, (warp + 1) * chunk);
+    for (int base = warp * chunk; base < j_end; base += 32) {
+      const int j = base + lane;
+      const bool act = j < j_end;
+      int kj = -1;
+      double gj = 0.0;
+      double e[KT];
+      if (act) {
+        kj = m.key[j];
+        const double eps_j = noi[j];
+        double ll;
+        const double *bj = B + (m.bot0 * m.C) * m.K + kj * m.K;
+        if (KT == 1) {
+          ll = bj[0];
+          e[0] = 1.0;
+        } else {
+          ll = 0.0;
+          const double *Ej = m.E + (size_t)j * m.K;
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            e[k] = (k < m.K) ? Ej[k] : 0.0;
+            if (k < m.K) ll += bj[k] * e[k];
+          }
+        }
+        double psi_j = 0.0, Wpsi = 0.0, deg = 0.0;
+        if (m.car) {
+          psi_j = psi[j];
+          const int r0 = m.rowptr[j], r1 = m.rowptr[j + 1];
+          for (int r = r0; r < r1; ++r) Wpsi += psi[m.col[r]];
+          deg = (double)(r1 - r0);
+          ll += psi_j;
+        }
+        ll += sig03 * eps_j;
+        const double eta = ll + m.lsf[j];
+        const double mu = exp(eta);
+        const int y = gn.counts[j];
+        if (m.zi && y == 0) {
+          // log_sum_exp(log theta, log1m theta - mu) and its softmax weights
+          const double Bq = tails - mu;
+          const double dd = heads - Bq;
+          const double t = exp(-fabs(dd));
+          const double l1p = log1p(t);
+          const double wmax = 1.0 / (1.0 + t), wmin = t / (1.0 + t);
+          const double wA = dd >= 0 ? wmax : wmin;
+          const double wB = dd >= 0 ? wmin : wmax;
+          a_lp += (dd >= 0 ? heads : Bq) + l1p;
+          gj = -wB * mu;
+          a_dth += wA / sc.theta - wB / (1.0 - sc.theta);
+        } else {
+          a_lp += (double)y * eta - mu;
+          gj = (double)y - mu;
+        }
+        a_lp -= 0.5 * eps_j * eps_j;
+        a_ng += eps_j * gj;
+        const double gr_eps = sig03 * gj - eps_j;
+        dg[m.o_noise + j] = -gr_eps;
+        a_g2 += gr_eps * gr_eps;
+        if (LEAP) {
+          const double pn = dp[m.o_noise + j] + 0.5 * eps * gr_eps;
+          dp[m.o_noise + j] = pn;
+          a_kin += minv[m.o_noise + j] * pn * pn;
+        }
+        if (m.car) {
+          a_qD += (psi_j * deg) * psi_j;
+          a_qW += Wpsi * psi_j;
+          const double gr_psi = gj - sc.tau * (deg * psi_j - sc.a * Wpsi);
+          dg[m.o_psi + j] = -gr_psi;
+          a_g2 += gr_psi * gr_psi;
+          if (LEAP) {
+            const double pn = dp[m.o_psi + j] + 0.5 * eps * gr_psi;
+            dp[m.o_psi + j] = pn;
+            a_kin += minv[m.o_psi + j] * pn * pn;
+          }
+        }
+      }
+      // bottom-level bins: per-lane run-length accumulation, warp-collective flush on change
+      const bool changed = act && (kj != cur_key) && (cur_key >= 0);
+      if (__any_sync(0xffffffffu, changed)) flush_bins(acc, cur_key);
+      if (act) {
+        cur_key = kj;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[k] += gj * e[k];
+      }
+    }
+    flush_bins(acc, cur_key);
+
+    // padding elements (Npad > N) carry q = p = g = 0
+    if (m.Npad > m.N && tid == 0) {
+      dg[m.o_noise + m.N] = 0.0;
+      if (LEAP) dp[m.o_noise + m.N] = 0.0;
+      if (m.car) { dg[m.o_psi + m.N] = 0.0; if (LEAP) dp[m.o_psi + m.N] = 0.0; }
+    }
+
+    // log-determinant term of the CAR prior over the distinct eigenvalues
+    double a_ldet = 0, a_dldet = 0;
+    if (m.car) {
+      for (int i = tid; i < m.n_eig; i += kBlock) {
+        const double lam = m.eigu[i], mult = m.eigm[i];
+        const double x = sc.a * lam;
+        a_ldet += mult * log1p(-x);
+        a_dldet += mult * (-lam / (1.0 - x));
+      }
+    }
+    // beta_raw ~ normal(0,1)
+    const double *sb = dq + m.o_small;
+    for (int idx = tid; idx < m.nbeta; idx += kBlock) a_lp -= 0.5 * sb[idx] * sb[idx];
+
+    double r1[9] = {a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_ldet, a_dldet, a_g2};
+    block_sum<9>(r1, red);  // also orders the shared atomics on adjB before the reads below
+
+    // reverse of the hierarchy (A.3): parents collect their children
+    const int CK = m.C * m.K;
+    if (m.L3) {
+      for (int idx = tid; idx < m.L2 * CK; idx += kBlock) {
+        const int i2 = idx / CK, rem = idx - i2 * CK;
+        double s = adjB[(m.L1 + i2) * CK + rem];
+        for (int i3 = 0; i3 < m.L3; ++i3)
+          if (m.map3[i3] == i2) s += adjB[(m.L1 + m.L2 + i3) * CK + rem];
+        adjB[(m.L1 + i2) * CK + rem] = s;
+      }
+      __syncthreads();
+    }
+    if (m.L2) {
+      for (int idx = tid; idx < m.L1 * CK; idx += kBlock) {
+        const int i1 = idx / CK, rem = idx - i1 * CK;
+        double s = adjB[i1 * CK + rem];
+        for (int i2 = 0; i2 < m.L2; ++i2)
+          if (m.map2[i2] == i1) s += adjB[(m.L1 + i2) * CK + rem];
+        adjB[i1 * CK + rem] = s;
+      }
+      __syncthreads();
+    }
+    double a_ds2 = 0, a_ds3 = 0, a_kin2 = 0, a_g2b = 0;
+    for (int idx = tid; idx < m.nbeta; idx += kBlock) {
+      const int i = idx / CK;
+      const double ab = adjB[idx], r = sb[idx];
+      double scale;
+      if (i < m.L1) scale = (m.family == 1) ? gn.ps[idx % m.K] : 2.0;
+      else if (i < m.L1 + m.L2) { scale = sc.s2; a_ds2 += ab * r; }
+      else { scale = sc.s3; a_ds3 += ab * r; }
+      const double gr = scale * ab - r;
+      dg[m.o_small + idx] = -gr;
+      a_g2b += gr * gr;
+      if (LEAP) {
+        const double pn = dp[m.o_small + idx] + 0.5 * eps * gr;
+        dp[m.o_small + idx] = pn;
+        a_kin2 += minv[m.o_small + idx] * pn * pn;
+      }
+    }
+    double r2[4] = {a_ds2, a_ds3, a_kin2, a_g2b};
+    block_sum<4>(r2, red);
+
+    // scalars: every thread computes them (uniform), thread 0 stores
+    double lp = r1[0] + sc.jac;
+    double kin = r1[5] + r2[2];
+    double g2 = r1[8] + r2[3];
+    const int so = m.o_small + m.nbeta;
+    double gu_tau = 0, gu_a = 0, gu_sigma, gu_s2 = 0, gu_s3 = 0, gu_theta = 0;
+    if (m.car) {
+      const double Q = r1[2] - sc.a * r1[3];
+      lp += -2.0 * log(sc.tau) - 1.0 / sc.tau;
+      lp += 0.5 * ((double)m.N * log(sc.tau) + r1[6] - sc.tau * Q);
+      const double d_tau = -2.0 / sc.tau + 1.0 / (sc.tau * sc.tau) + 0.5 * ((double)m.N / sc.tau - Q);
+      const double d_a = 0.5 * (r1[7] + sc.tau * r1[3]);
+      gu_tau = sc.tau * d_tau + (jacobian ? 1.0 : 0.0);
+      gu_a = sc.a * (1.0 - sc.a) * d_a + (jacobian ? (1.0 - 2.0 * sc.a) : 0.0);
+    }
+    lp += -0.5 * sc.sigma * sc.sigma;
+    gu_sigma = sc.sigma * (-sc.sigma + 0.3 * r1[1]) + (jacobian ? 1.0 : 0.0);
+    if (m.L2) { lp += -0.5 * sc.s2 * sc.s2; gu_s2 = sc.s2 * (-sc.s2 + r2[0]) + (jacobian ? 1.0 : 0.0); }
+    if (m.L3) { lp += -0.5 * sc.s3 * sc.s3; gu_s3 = sc.s3 * (-sc.s3 + r2[1]) + (jacobian ? 1.0 : 0.0); }
+    if (m.zi) {
+      lp += tails;                      // theta ~ beta(1,2)
+      lp += gn.nnz * tails - gn.lgam;   // bernoulli(0|theta) and -lgamma(y+1) of the non-zero spots
+      const double d_theta = r1[4] - (gn.nnz + 1.0) / (1.0 - sc.theta);
+      gu_theta = sc.theta * (1.0 - sc.theta) * d_theta + (jacobian ? (1.0 - 2.0 * sc.theta) : 0.0);
+    }
+    // read phase (all threads) then write phase (thread 0) of the scalar momenta
+    double pn_s[6] = {0, 0, 0, 0, 0, 0};
+    const double gu[6] = {gu_tau, gu_a, gu_sigma, gu_s2, gu_s3, gu_theta};
+    const int sidx[6] = {m.s_tau, m.s_a, m.s_sigma, m.s_s2, m.s_s3, m.s_theta};
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      if (sidx[s] >= 0) {
+        g2 += gu[s] * gu[s];
+        if (LEAP) {
+          pn_s[s] = dp[so + sidx[s]] + 0.5 * eps * gu[s];
+          kin += minv[so + sidx[s]] * pn_s[s] * pn_s[s];
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+        if (sidx[s] >= 0) {
+          dg[so + sidx[s]] = -gu[s];
+          if (LEAP) dp[so + sidx[s]] = pn_s[s];
+        }
+      }
+      for (int s = m.nsmall; s < m.nsmall_pad; ++s) {
+        dg[m.o_small + s] = 0.0;
+        if (LEAP) dp[m.o_small + s] = 0.0;
+      }
+    }
+    __syncthreads();
+    if (V_out) *V_out = -lp;
+    if (K_out) *K_out = 0.5 * kin;
+    if (finite_out) *finite_out = isfinite(lp) && isfinite(g2);
+  }
+
+  // ---- Ops interface of nuts_core.h ---------------------------------------------------------------
+  __device__ double sample_momentum(int pv, uint32_t purpose, uint32_t sub, uint32_t iter) {
+    double *p = vec(pv);
+    double k = 0.0;
+    for (int e = threadIdx.x; e < m.Di; e += kBlock) {
+      const int si = m.imap[e];
+      double v = 0.0;
+      if (si >= 0) {
+        const double mi = minv[e];
+        v = rng_normal(key, purpose, sub, iter, (uint32_t)si) / sqrt(mi);
+        k += mi * v * v;
+      }
+      p[e] = v;
+    }
+    double r[1] = {k};
+    block_sum<1>(r, red);
+    sample_is_q0 = true;
+    return 0.5 * r[0];
+  }
+  __device__ double eval_at_current(int z, bool *finite) {
+    double V;
+    eval<false>(q_cur, nullptr, nullptr, zq[z], zg[z], nullptr, 0.0, &V, nullptr, finite);
+    return V;
+  }
+  __device__ void leapfrog(int zs, int ps, int zd, int pd, double eps, double *V, double *K) {
+    eval<true>(zq[zs], zg[zs], vec(ps), zq[zd], zg[zd], vec(pd), eps, V, K, nullptr);
+  }
+  // Stan's three generalised U-turn criteria for the subtree L ++ C (base_nuts.hpp
+  // build_tree / transition) as six metric-weighted inner products in one pass.
+  __device__ bool merge(SubTree L, SubTree C, int rho_out) {
+    const double *Lpb = vec(L.pb), *Lpe = vec(L.pe), *Lrho = vec(L.rho);
+    const double *Cpb = vec(C.pb), *Cpe = vec(C.pe), *Crho = vec(C.rho);
+    double *out = vec(rho_out);
+    double a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0;
+    for (int e = 2 * threadIdx.x; e < m.Di; e += 2 * kBlock) {
+      const double2 w = *reinterpret_cast<const double2 *>(minv + e);
+      const double2 lpb = *reinterpret_cast<const double2 *>(Lpb + e);
+      const double2 lpe = *reinterpret_cast<const double2 *>(Lpe + e);
+      const double2 lrh = *reinterpret_cast<const double2 *>(Lrho + e);
+      const double2 cpb = *reinterpret_cast<const double2 *>(Cpb + e);
+      const double2 cpe = *reinterpret_cast<const double2 *>(Cpe + e);
+      const double2 crh = *reinterpret_cast<const double2 *>(Crho + e);
+      double2 rs;
+      rs.x = lrh.x + crh.x;
+      rs.y = lrh.y + crh.y;
+      a1 += (w.x * lpb.x) * rs.x + (w.y * lpb.y) * rs.y;
+      a2 += (w.x * cpe.x) * rs.x + (w.y * cpe.y) * rs.y;
+      const double rbx = lrh.x + cpb.x, rby = lrh.y + cpb.y;
+      b1 += (w.x * lpb.x) * rbx + (w.y * lpb.y) * rby;
+      b2 += (w.x * cpb.x) * rbx + (w.y * cpb.y) * rby;
+      const double rcx = crh.x + lpe.x, rcy = crh.y + lpe.y;
+      c1 += (w.x * lpe.x) * rcx + (w.y * lpe.y) * rcy;
+      c2 += (w.x * cpe.x) * rcx + (w.y * cpe.y) * rcy;
+      *reinterpret_cast<double2 *>(out + e) = rs;
+    }
+    double r[6] = {a1, a2, b1, b2, c1, c2};
+    block_sum<6>(r, red);
+    return (r[1] > 0 && r[0] > 0) && (r[3] > 0 && r[2] > 0) && (r[5] > 0 && r[4] > 0);
+  }
+  __device__ void copy_vec(double *dst, const double *src) {
+    for (int e = 2 * threadIdx.x; e < m.Di; e += 2 * kBlock)
+      *reinterpret_cast<double2 *>(dst + e) = *reinterpret_cast<const double2 *>(src + e);
+    __syncthreads();
+  }
+  __device__ void copy_q_to_prop(int z) { copy_vec(q_prop, zq[z]); }
+  __device__ void swap_prop_sample() {
+    double *t = q_prop;
+    q_prop = q_samp;
+    q_samp = t;
+    sample_is_q0 = false;
+  }
+  __device__ void commit_sample() {
+    if (!sample_is_q0) copy_vec(q_cur, q_samp);
+  }
+  __device__ void init_uniform(uint32_t attempt, double radius) {
+    for (int e = threadIdx.x; e < m.Di; e += kBlock) {
+      const int si = m.imap[e];
+      q_cur[e] = si >= 0 ? rng_init(key, attempt, (uint32_t)si, radius) : 0.0;
+    }
+    __syncthreads();
+  }
+  __device__ void set_unit_metric() {
+    for (int e = threadIdx.x; e < m.Di; e += kBlock) { minv[e] = 1.0; wm[e] = 0.0; wm2[e] = 0.0; }
+    __syncthreads();
+  }
+  __device__ void welford_add(double n) {
+    for (int e = threadIdx.x; e < m.Di; e += kBlock) {
+      const double q = q_cur[e];
+      const double delta = q - wm[e];
+      const double mean = wm[e] + delta / n;
+      wm[e] = mean;
+      wm2[e] += (q - mean) * delta;
+    }
+    __syncthreads();
+  }
+  __device__ void metric_update(double n) {
+    for (int e = threadIdx.x; e < m.Di; e += kBlock) {
+      double v = minv[e];
+      if (n > 1) v = wm2[e] / (n - 1.0);
+      minv[e] = (m.imap[e] >= 0) ? (n / (n + 5.0)) * v + 1e-3 * (5.0 / (n + 5.0)) : 1.0;
+      wm[e] = 0.0;
+      wm2[e] = 0.0;
+    }
+    __syncthreads();
+  }
+  // one sampling draw: sampler columns, the small block, optional full theta, and the streaming
+  // summaries summarize_stan_hdf5 needs (/root/reference/splotch/utils.py:234-257)
+  __device__ void record_draw(const DrawInfo &info, int s) {
+    const int tid = threadIdx.x;
+    if (out_diag && tid == 0) {
+      double *r = out_diag + (size_t)s * 7;
+      r[0] = info.lp; r[1] = info.accept_stat; r[2] = info.stepsize; r[3] = info.treedepth;
+      r[4] = info.n_leapfrog; r[5] = info.divergent; r[6] = info.energy;
+    }
+    if (out_small)
+      for (int i = tid; i < m.nsmall; i += kBlock) out_small[(size_t)s * m.nsmall + i] = q_cur[m.o_small + i];
+    if (out_theta)
+      for (int e = tid; e < m.Di; e += kBlock) {
+        const int si = m.imap[e];
+        if (si >= 0) out_theta[(size_t)s * m.D + si] = q_cur[e];
+      }
+    if (out_summ) {
+      Scalars sc;
+      load_small(q_cur, sc);
+      const double n = (double)(s + 1);
+      const double sig03 = 0.3 * sc.sigma;
+      double *mll = out_summ, *vll = out_summ + m.N, *mla = out_summ + 2 * (size_t)m.N,
+             *vla = out_summ + 3 * (size_t)m.N, *mps = out_summ + 4 * (size_t)m.N,
+             *vps = out_summ + 5 * (size_t)m.N;
+      for (int j = tid; j < m.N; j += kBlock) {
+        const double *bj = B + (m.bot0 * m.C) * m.K + m.key[j] * m.K;
+        double ll;
+        if (KT == 1) {
+          ll = bj[0];
+        } else {
+          ll = 0.0;
+          const double *Ej = m.E + (size_t)j * m.K;
+          for (int k = 0; k < m.K; ++k) ll += bj[k] * Ej[k];
+        }
+        double psi_j = 0.0;
+        if (m.car) { psi_j = q_cur[m.o_psi + j]; ll += psi_j; }
+        ll += sig03 * q_cur[m.o_noise + j];
+        double d = ll - mll[j], mean = mll[j] + d / n;
+        mll[j] = mean; vll[j] += (ll - mean) * d;
+        const double la = exp(ll);
+        d = la - mla[j]; mean = mla[j] + d / n;
+        mla[j] = mean; vla[j] += (la - mean) * d;
+        if (m.car) {
+          d = psi_j - mps[j]; mean = mps[j] + d / n;
+          mps[j] = mean; vps[j] += (psi_j - mean) * d;
+        }
+      }
+    }
+    __syncthreads();
+  }
+};
+
+}  // namespace csp
