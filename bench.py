@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — gradient evaluations / second of batched NUTS over genes x chains (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+
+One "step" advances EVERY resident gene-chain of the workload by `--iters` NUTS transitions
+(one launch of the persistent kernel).  W untimed steps, then exactly K timed steps bracketed by a
+barrier + device synchronise; device time from CUDA events on the sampler's stream, max over ranks.
+
+  value      gradient evaluations / s, whole job (all ranks), inputs resident in HBM
+  e2e        same metric through the host-buffer C ABI: counts H2D, sampler create + advance, draws and
+             spot summaries D2H, all inside the timed region
+  roofline   dominant kernel k_nuts_advance: algorithmic bytes (B_leap = 56 D + 4 N per
+             in-sampler leapfrog, B_grad = 16 D + 4 N per other gradient) / CUDA-event duration vs the
+             measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (restatement of the Stan models + Stan's NUTS; CmdStan itself is not
+             installable here) on all host cores, bounded sample, rank 0 at N=1
+
+`--impl reference` times that same CPU implementation (all host threads) on this arm's config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grad_evals_per_sec"
+UNIT = "grad-evals/s"
+
+WORKLOADS = {
+    # name: (config key, genes per GPU by default, iterations per step, description)
+    "c2": ("c2", 11313, 2, "c2: examples/ ST-v1 geometry, splotch_stan_model 2-level Poisson+CAR, N=2473 spots, "
+                           "D=5016, all 11313 genes x 4 chains"),
+    "c3": ("c3", 592, 1, "c3: synthetic Visium 24x4992 spots, comp_splotch_stan_model 3-level ZIP+CAR K=10, "
+                         "D=242142, gene slice x 4 chains"),
+    "c4": ("c4", 148, 1, "c4: synthetic Visium-HD 4x317^2 bins, splotch_stan_model_csr 2-level ZIP+CAR, D=803989, "
+                         "gene slice x 4 chains"),
+    "c5": ("c5", 592, 1, "c5: c3 covariates, 32768-gene sweep sharded over the GPUs (slice per GPU) x 4 chains"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(workload: str, genes_per_gpu: int, rank: int):
+    from csplotch_b200 import synth
+    key = WORKLOADS[workload][0]
+    cfg = synth.CONFIGS[key]
+    shared = cfg["shared"]()
+    # every rank owns a different slice of the gene list (seeded by global gene index block)
+    genes = synth.simulate_counts(shared, genes_per_gpu, cfg["seed"] + 1000 * rank, chunk=max(16, (1 << 22) // int(np.sum(shared["N_spots"]))))
+    return cfg["family"], shared, genes
+
+
+def cpu_reference_run(family, shared, genes, iters, n_threads, seconds_target=15.0, n_chains=4):
+    """Bounded CPU sample: n_threads gene-chains (one thread each, like CmdStan's one process per
+    chain) for `iters` warm-up transitions from initialisation; returns (grads, seconds, description)."""
+    import oracle
+    from csplotch_b200 import synth
+    G = max(1, n_threads // n_chains)
+    G = min(G, genes["counts"].shape[0])
+    o = oracle.Oracle(synth.gene_dict(shared, genes, 0), family)
+    cfg = oracle.nuts_cfg(iters, 0, seed=1)
+    t0 = time.time()
+    res = o.nuts_batch(genes["counts"][:G], cfg, n_chains=n_chains, prior_mean=genes.get("beta_prior_mean", [None])[:G] if "beta_prior_mean" in genes else None,
+                       prior_std=genes["beta_prior_std"][:G] if "beta_prior_std" in genes else None,
+                       n_threads=n_threads, want_draws=False)
+    dt = time.time() - t0
+    return res["n_grad"], dt, "%d genes x %d chains x first %d NUTS transitions (from initialisation)" % (G, n_chains, iters)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores.  CmdStan is
+    not installable in this image (no stanc / Stan Math / network), so this is the C restatement in
+    oracle/ (kind "port"), gene-parallel over all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    family, shared, genes = make_inputs(args.workload, max(8, (os.cpu_count() or 8) // 4), 0)
+    nthr = os.cpu_count() or 1
+    N = int(np.sum(shared["N_spots"]))
+    iters = args.cpu_iters or (4 if N < 10000 else 1)
+    for _ in range(args.warmup):
+        cpu_reference_run(family, shared, genes, 1, nthr)
+    tot_g, tot_t, sample = 0, 0.0, ""
+    for _ in range(args.steps):
+        g, dt, sample = cpu_reference_run(family, shared, genes, iters, nthr)
+        tot_g += g; tot_t += dt
+    val = tot_g / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][3]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port", "sample": "per step: " + sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of the Stan models + Stan NUTS (oracle/), not CmdStan: CmdStan cannot be built here",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--genes", type=int, default=0, help="genes per GPU (default: the workload's)")
+    ap.add_argument("--iters", type=int, default=0, help="NUTS transitions per chain per step")
+    ap.add_argument("--chains", type=int, default=4)
+    ap.add_argument("--cpu-iters", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-genes", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 3) if os.environ.get("CSPLOTCH_BENCH_STRICT", "1") == "1" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from csplotch_b200 import api, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    api.check(_lib.lib().csplotch_set_device(local))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = WORKLOADS[args.workload]
+    G = args.genes or wl[1]
+    iters = args.iters or wl[2]
+    family, shared, genes = make_inputs(args.workload, G, rank)
+    model = api.Model(shared, family)
+    N, D = model.N, model.dim
+    B_leap, B_grad = 56 * D + 4 * N, 16 * D + 4 * N
+
+    # ---- resident arm: inputs already in HBM ------------------------------------------------------
+    batch = api.Batch(model, genes["counts"], genes.get("beta_prior_mean"), genes.get("beta_prior_std"),
+                      gene_id0=rank * G)
+    total_iters = (args.warmup + args.steps) * iters
+    scfg = api.nuts_cfg(total_iters, 0, args.chains, seed=20240)   # all steps fall in Stan's warm-up phase
+    sampler = api.Sampler(batch, scfg)
+    for _ in range(args.warmup):
+        sampler.advance(iters, sync=True)
+    c0 = sampler.counters()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ms_dev = 0.0
+    per_step = []
+    t_wall0 = time.time()
+    for _ in range(args.steps):
+        sampler.advance(iters, sync=True)
+        ms = sampler.last_ms()
+        per_step.append(ms)
+        ms_dev += ms
+    barrier()
+    t_wall = time.time() - t_wall0
+    clk = clocks.stop() if rank == 0 else None
+    c1 = sampler.counters()
+    grads = c1["n_grad"] - c0["n_grad"]
+    leaps = c1["n_leapfrog"] - c0["n_leapfrog"]
+    launches = c1["n_launches"] - c0["n_launches"]
+    del sampler
+
+    # ---- e2e arm: host buffers through the C ABI, copies inside the timed region --------------------
+    Ge = args.e2e_genes or min(G, 148 if N < 10000 else 74)
+    e2e_iters = max(iters, 2)
+    counts_host = np.ascontiguousarray(genes["counts"][:Ge])
+    pm = genes["beta_prior_mean"][:Ge] if "beta_prior_mean" in genes else None
+    ps = genes["beta_prior_std"][:Ge] if "beta_prior_std" in genes else None
+
+    def e2e_step():
+        b = api.Batch(model, counts_host, pm, ps, gene_id0=rank * G)       # H2D of this step's inputs
+        s = api.Sampler(b, api.nuts_cfg(e2e_iters // 2, e2e_iters - e2e_iters // 2, args.chains, seed=7))
+        s.run()
+        diag, small, nd = s.draws()                                       # D2H of the step's results
+        summ = s.spot_summaries()
+        cnt = s.counters()
+        d2h = diag.nbytes + small.nbytes + nd.nbytes + sum(v.nbytes for v in summ.values())
+        s.close(); b.close()
+        return cnt["n_grad"], counts_host.nbytes + (pm.nbytes + ps.nbytes if pm is not None else 0), d2h
+
+    e2e_step()
+    barrier()
+    t0 = time.time()
+    e_grads, h2d, d2h = 0, 0, 0
+    e_steps = max(2, min(args.steps, 4))
+    for _ in range(e_steps):
+        g, a, b_ = e2e_step()
+        e_grads += g; h2d = a; d2h = b_
+    barrier()
+    e_dt = time.time() - t0
+
+    # ---- reduce over ranks ---------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms_dev, e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, e_dt = float(t[0]), float(t[1])
+        t = torch.tensor([grads, leaps, e_grads, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        grads, leaps, e_grads, launches = (float(x) for x in t)
+    value = grads / (ms_dev * 1e-3)
+    e2e_value = e_grads / e_dt
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = (leaps * B_leap + (grads - leaps) * B_grad) / max(1, world)   # per GPU
+        achieved = alg_bytes / (ms_dev * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_grad", 0) * (grads / max(1, world)) / max(1, args.steps) or None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl[3], "genes_per_gpu": G, "chains": args.chains,
+                       "nuts_transitions_per_chain_per_step": iters,
+                       "l2_policy": "inputs larger than L2: %.1f GB of chain state per GPU streamed every step"
+                                    % ((4 * model.dim * 8 * G * args.chains) / 1e9),
+                       "phase": "Stan warm-up transitions %d..%d of every chain (adaptive NUTS, max_depth 10)"
+                                % (args.warmup * iters, total_iters)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": "%d genes x %d chains: Batch(host counts) -> Sampler %d transitions -> draws + spot "
+                            "summaries to host, per step, through the C ABI" % (Ge, args.chains, e2e_iters)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_nuts_advance",
+                         "algorithmic_bytes_per_leapfrog": B_leap, "algorithmic_bytes_per_gradient": B_grad,
+                         "launches": int(launches / max(1, world)), "avg_launch_ms": ms_dev / max(1, args.steps)},
+            "clocks": clk,
+            "leapfrogs": leaps, "grad_evals": grads, "wall_s": t_wall,
+        }
+        if world == 1 and not args.no_cpu:
+            nthr = os.cpu_count() or 1
+            cg, cdt, sample = cpu_reference_run(family, shared, genes, args.cpu_iters or (4 if N < 10000 else 1), nthr)
+            line["cpu_baseline"] = {"value": cg / cdt, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample,
+                                    "seconds": cdt,
+                                    "note": "CPU restatement (oracle/), not CmdStan: CmdStan cannot be built in this image"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,184 @@
+"""`splotch` — same flags as the reference wrapper (/root/reference/bin/splotch:9-29):
+
+    splotch -g GENE_IDX -d DATA_DIRECTORY -o OUTPUT_DIRECTORY -b BINARY -n NUM_SAMPLES -c NUM_CHAINS [-s]
+
+`-b BINARY`: the basename (splotch_stan_model | comp_splotch_stan_model | splotch_stan_model_csr) selects
+the model family; no CmdStan executable is run.  Additive: `-g` also accepts ranges / lists
+("1-2000", "3,7,9-12") so one process samples thousands of genes at once on the GPU, `--gpus N` shards the
+gene list over N devices (one process each, no collective), `--seed`.
+
+Inputs are the unchanged `DATA/<g//100>/data_<g>.R` files of splotch_generate_input_files; outputs are
+`OUT/<g//100>/combined_<g>.csv` (header + draws, chain-major, no comments) or, with -s,
+`combined_<g>.hdf5` (summary layout of summarize_stan_hdf5; .npz with the same keys without h5py).
+
+`cmdstan_shim` accepts the argv contract of the CmdStan executable itself
+(`BINARY sample num_samples=N num_warmup=N random id=CHAIN data file=IN.R output file=OUT.csv`) so that the
+unmodified reference `bin/splotch` also works with `-b <shim named like the model>`.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from . import rdump, stancsv
+
+
+def parse_genes(spec: str):
+    out = []
+    for part in str(spec).split(","):
+        part = part.strip()
+        if not part:
+            continue
+        if "-" in part[1:]:
+            a, b = part.split("-", 1)
+            out.extend(range(int(a), int(b) + 1))
+        else:
+            out.append(int(part))
+    return out
+
+
+def data_path(data_dir: str, g: int) -> str:
+    return os.path.join(data_dir, str(g // 100), "data_%d.R" % g)
+
+
+def load_genes(data_dir: str, gene_ids):
+    """Shared covariates parsed once; only counts / beta priors from every other file."""
+    first = rdump.read_rdump(data_path(data_dir, gene_ids[0]))
+    shared = {k: v for k, v in first.items() if k not in rdump.GENE_KEYS}
+    counts, pm, ps = [], [], []
+    for i, g in enumerate(gene_ids):
+        d = first if i == 0 else rdump.read_rdump_gene_only(data_path(data_dir, g))
+        counts.append(np.asarray(d["counts"], dtype=np.int32))
+        if "beta_prior_mean" in d:
+            pm.append(np.asarray(d["beta_prior_mean"], dtype=np.float64))
+            ps.append(np.asarray(d["beta_prior_std"], dtype=np.float64))
+    genes = {"counts": np.stack(counts)}
+    if pm:
+        genes["beta_prior_mean"] = np.stack(pm)
+        genes["beta_prior_std"] = np.stack(ps)
+    return shared, genes
+
+
+def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chains, summary, seed=0,
+                 num_warmup=None, device=0):
+    from . import api, _lib
+    api.check(_lib.lib().csplotch_set_device(device))
+    model = api.Model(shared, family)
+    fam = api.family_from_binary(family)
+    batch = api.Batch(model, genes["counts"], genes.get("beta_prior_mean") if fam == 1 else None,
+                      genes.get("beta_prior_std") if fam == 1 else None, gene_id0=int(gene_ids[0]))
+    nw = num_samples if num_warmup is None else num_warmup          # bin/splotch:131 num_warmup=num_samples
+    cfg = api.nuts_cfg(nw, num_samples, num_chains, seed=seed, keep_draws=not summary)
+    s = api.Sampler(batch, cfg).run(chunk=50)
+    status, iters = s.status()
+    cols = model.column_names()
+    written = []
+    theta = s.theta_draws() if not summary else None
+    diag, _, _ = s.draws()
+    for i, g in enumerate(gene_ids):
+        if (status[i] != 0).any():
+            # a failed chain: like a failed CmdStan run, no output file for this gene (error_exit, bin/splotch:131)
+            print("Error: sampling failed for gene %d (status %s)" % (g, status[i].tolist()), file=sys.stderr)
+            continue
+        d = os.path.join(out_dir, str(g // 100))
+        os.makedirs(d, exist_ok=True)
+        if summary:
+            written.append(stancsv.write_summary(os.path.join(d, "combined_%d.hdf5" % g),
+                                                 stancsv.summary_from_sampler(s, i)))
+        else:
+            th = theta[i].reshape(-1, model.dim)
+            vals = batch.write_array(th, gene_of=np.full(len(th), i, dtype=np.int32))
+            p = os.path.join(d, "combined_%d.csv" % g)
+            stancsv.write_combined_csv(p, cols, diag[i].reshape(-1, 7), vals)
+            written.append(p)
+    return written, s
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="splotch", description="A wrapper for running Splotch (B200-native sampler)")
+    ap.add_argument("-g", required=True, help="gene index (1-based); ranges/lists allowed: 1-100,205")
+    ap.add_argument("-d", required=True, help="data directory")
+    ap.add_argument("-o", required=True, help="output directory")
+    ap.add_argument("-b", required=True, help="Splotch binary (its basename selects the model)")
+    ap.add_argument("-n", required=True, type=int, help="number of samples")
+    ap.add_argument("-c", required=True, type=int, help="number of chains")
+    ap.add_argument("-s", action="store_true", help="store summary rather than full output")
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=512, help="genes resident on the GPU at once")
+    ap.add_argument("--device", type=int, default=0)
+    a = ap.parse_args(argv)
+    gene_ids = parse_genes(a.g)
+    seed = a.seed if a.seed is not None else (int.from_bytes(os.urandom(4), "little"))   # CmdStan seeds from the clock
+    if not os.path.isdir(a.d):
+        print("Error: data directory does not exist!", file=sys.stderr)
+        return 1
+    try:
+        os.makedirs(a.o, exist_ok=True)
+    except OSError:
+        print("Error: Cannot create the output directory!", file=sys.stderr)
+        return 1
+    # contiguous runs keep gene_id0 + i == gene id (RNG stream keyed by the gene index)
+    runs, cur = [], [gene_ids[0]]
+    for g in gene_ids[1:]:
+        if g == cur[-1] + 1 and len(cur) < a.batch:
+            cur.append(g)
+        else:
+            runs.append(cur); cur = [g]
+    runs.append(cur)
+    rc = 0
+    for run in runs:
+        try:
+            shared, genes = load_genes(a.d, run)
+            sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device)
+        except Exception as e:  # noqa: BLE001
+            print("Error: Stan run failed! (%s)" % e, file=sys.stderr)
+            rc = 1
+    return rc
+
+
+def cmdstan_shim(argv=None, family=None):
+    """argv contract of the CmdStan executable (bin/splotch:131, bin/splotch_vinit:194)."""
+    argv = list(sys.argv if argv is None else argv)
+    family = family or os.path.basename(argv[0])
+    args = argv[1:]
+    if not args or args[0] != "sample":
+        print("only the `sample` method is supported", file=sys.stderr)
+        return 1
+    kv = {}
+    section = None
+    for tok in args[1:]:
+        if "=" in tok:
+            k, v = tok.split("=", 1)
+            kv[(section + "." + k) if section in ("data", "output", "random") and k in ("file", "id", "seed") else k] = v
+        else:
+            section = tok
+    num_samples = int(kv.get("num_samples", 1000))
+    num_warmup = int(kv.get("num_warmup", 1000))
+    chain_id = int(kv.get("random.id", kv.get("id", 1)))
+    seed = int(kv.get("random.seed", kv.get("seed", int.from_bytes(os.urandom(4), "little"))))
+    data = rdump.read_rdump(kv["data.file"])
+    from . import api
+    shared = {k: v for k, v in data.items() if k not in rdump.GENE_KEYS}
+    model = api.Model(shared, family)
+    fam = api.family_from_binary(family)
+    batch = api.Batch(model, np.asarray(data["counts"])[None], data.get("beta_prior_mean") if fam == 1 else None,
+                      data.get("beta_prior_std") if fam == 1 else None)
+    # one chain per process like CmdStan; chain ids start at 1, so run chain_id chains' worth of keying
+    cfg = api.nuts_cfg(num_warmup, num_samples, 1, seed=seed + 7919 * (chain_id - 1), keep_draws=True)
+    s = api.Sampler(batch, cfg).run(chunk=50)
+    st, _ = s.status()
+    if (st != 0).any():
+        return 1
+    diag, _, _ = s.draws()
+    th = s.theta_draws()[0, 0]
+    vals = batch.write_array(th, gene_of=np.zeros(len(th), dtype=np.int32))
+    out = kv.get("output.file", "output.csv")
+    stancsv.write_combined_csv(out, model.column_names(), diag[0, 0], vals)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

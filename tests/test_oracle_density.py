@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 from csplotch_b200 import synth
-from stan_transcript import stan_log_prob_grad
+from tests.stan_transcript import stan_log_prob_grad
 
 FAMS = ["splotch_stan_model", "comp_splotch_stan_model", "splotch_stan_model_csr"]
 
