@@ -291,6 +291,12 @@ class Sampler:
         check(self.lib.csplotch_sampler_counters(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(n_leapfrog=a.value, n_grad=b.value, n_divergent=c.value, n_launches=d.value)
 
+    def profile(self):
+        out = (C.c_int64 * 6)()
+        check(self.lib.csplotch_sampler_profile(self.h, out))
+        keys = ["cyc_eval", "cyc_merge", "cyc_copy", "cyc_other", "n_merge", "n_copy"]
+        return dict(zip(keys, [int(x) for x in out]))
+
     def status(self):
         st = np.zeros((self.G, self.nch), dtype=np.int32)
         it = np.zeros((self.G, self.nch), dtype=np.int32)

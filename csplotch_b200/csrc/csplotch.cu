@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -195,11 +196,32 @@ __global__ void k_summ_finalize(const double *__restrict__ summ, const ChainScal
 // ------------------------------------------------------------------------------------------------
 // main kernels
 // ------------------------------------------------------------------------------------------------
+// dynamic shared memory: B[nbeta] | adjB[nbeta] | red | mbar[4] | ring[4T] | phr[2T] | mst[2T] | psi slots | rest slots
 template <int KT>
 __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, double *smem) {
   ops.B = smem;
   ops.adjB = smem + m.nbeta;
   ops.red = smem + 2 * m.nbeta;
+  double *p = ops.red + kWarps * kRedMax;
+  ops.mbar = reinterpret_cast<uint64_t *>(p);
+  p += 4;
+  ops.ring = p;
+  p += 4 * kTile;
+  ops.phr = p;
+  p += 2 * kTile;
+  ops.mst = p;
+  p += 2 * kTile;
+  ops.psi_st = p;
+  p += 8 * kTile;
+  ops.rest_st = reinterpret_cast<unsigned char *>(p);
+  ops.tile_seq = 0;
+  if (m.tiled) {
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 4; ++i) mbar_init(ops.mbar + i, 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
 }
 
 template <int KT>
@@ -208,7 +230,7 @@ k_lpgrad(const __grid_constant__ DevModel m, const int *__restrict__ counts, con
          const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz, int G,
          const double *__restrict__ theta_int, const int *__restrict__ gene_of, int Bn, double *lp_out,
          double *grad_int, int jacobian) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   DevOps<KT> ops(m);
   bind_smem(ops, m, smem);
   ops.jacobian = jacobian;
@@ -241,7 +263,7 @@ k_leapfrog_fixed(const __grid_constant__ DevModel m, const int *__restrict__ cou
                  const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz,
                  int G, double *q, double *p, double *g, const double *__restrict__ minv,
                  const int *__restrict__ gene_of, int Bn, double eps, int n_steps, double *H_out) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   DevOps<KT> ops(m);
   bind_smem(ops, m, smem);
   ops.jacobian = 1;
@@ -273,10 +295,13 @@ k_leapfrog_fixed(const __grid_constant__ DevModel m, const int *__restrict__ cou
 template <int KT>
 __global__ void __launch_bounds__(kBlock, 2)
 k_nuts_advance(const __grid_constant__ DevModel m, const __grid_constant__ SamplerDev s, int n_iter) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ int s_work;
   const size_t Di = m.Di;
   double *ws = s.ws + (size_t)blockIdx.x * (size_t)(kPoolVecs + 6) * Di;
+  DevOps<KT> ops(m);
+  bind_smem(ops, m, smem);
+  ops.jacobian = 1;
   for (;;) {
     if (threadIdx.x == 0) s_work = atomicAdd(s.queue, 1);
     __syncthreads();
@@ -284,9 +309,6 @@ k_nuts_advance(const __grid_constant__ DevModel m, const __grid_constant__ Sampl
     __syncthreads();
     if (w >= s.W) break;
     const int g = w / s.num_chains, c = w - g * s.num_chains;
-    DevOps<KT> ops(m);
-    bind_smem(ops, m, smem);
-    ops.jacobian = 1;
     ops.gn.counts = s.counts + (size_t)g * m.Nc;
     ops.gn.pm = s.pm ? s.pm + (size_t)g * m.K : nullptr;
     ops.gn.ps = s.ps ? s.ps + (size_t)g * m.K : nullptr;
@@ -311,10 +333,17 @@ k_nuts_advance(const __grid_constant__ DevModel m, const __grid_constant__ Sampl
     ops.out_theta = s.theta ? s.theta + (size_t)w * ns * m.D : nullptr;
     ops.out_summ = s.summ ? s.summ + (size_t)w * 6 * m.N : nullptr;
     ChainScalars cs = s.cs[w];
+    ops.cyc_eval = ops.cyc_merge = ops.cyc_copy = ops.cyc_other = ops.n_merge = ops.n_copy = 0;
+    const long long t_chain = clock64();
     Nuts<DevOps<KT>> nuts(ops, s.cfg, cs, ops.key);
     nuts.advance(n_iter, s.have_init != 0);
     __syncthreads();
-    if (threadIdx.x == 0) s.cs[w] = cs;
+    if (threadIdx.x == 0) {
+      cs.cyc_eval += ops.cyc_eval; cs.cyc_merge += ops.cyc_merge; cs.cyc_copy += ops.cyc_copy;
+      cs.n_merge += ops.n_merge; cs.n_copy += ops.n_copy;
+      cs.cyc_other += (clock64() - t_chain) - ops.cyc_eval - ops.cyc_merge - ops.cyc_copy;
+      s.cs[w] = cs;
+    }
   }
 }
 
@@ -375,7 +404,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   m->kt = kt;
   DevModel &dm = m->dm;
   memset(&dm, 0, sizeof(dm));
-  dm.family = d->family; dm.N = N; dm.Npad = (N + 1) & ~1; dm.C = C; dm.K = K;
+  dm.family = d->family; dm.N = N; dm.NT = (N + kTile - 1) / kTile; dm.Npad = dm.NT * kTile; dm.C = C; dm.K = K;
   dm.L1 = L1; dm.L2 = L2; dm.L3 = L3; dm.L = L;
   dm.bot0 = L3 ? L1 + L2 : (L2 ? L1 : 0);
   dm.nbeta = L * C * K;
@@ -395,19 +424,110 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   dm.o_small = dm.o_noise + dm.Npad;
   dm.Di = dm.o_small + dm.nsmall_pad;
   dm.D = (car ? N : 0) + dm.nbeta + ns + N;
-  dm.Nc = (N + 3) & ~3;
+  dm.Nc = dm.Npad;
   m->n_outputs = dm.D + N + dm.nbeta;
-  m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax) * sizeof(double);
-  if (m->smem_bytes > 200 * 1024) {
+
+  // ---- adjacency in original spot ids ---------------------------------------------------------------
+  std::vector<std::vector<int>> adj0(car ? N : 0);
+  if (car) {
+    if (!d->eig_values) { delete m; return fail(CSPLOTCH_E_INVALID, "car=1 needs eig_values"); }
+    if (d->U && d->V) {
+      for (int i = 0; i < N; ++i)
+        for (int e = d->U[i] - 1; e < d->U[i + 1] - 1; ++e) {
+          const int nb = d->V[e] - 1;
+          if (nb < 0 || nb >= N) { delete m; return fail(CSPLOTCH_E_INVALID, "V out of range"); }
+          adj0[i].push_back(nb);
+        }
+    } else if (d->W_sparse) {
+      for (int e = 0; e < d->W_n; ++e) {
+        const int a = d->W_sparse[2 * e] - 1, b = d->W_sparse[2 * e + 1] - 1;
+        if (a < 0 || a >= N || b < 0 || b >= N) { delete m; return fail(CSPLOTCH_E_INVALID, "W_sparse out of range"); }
+        adj0[a].push_back(b);
+        adj0[b].push_back(a);
+      }
+    } else {
+      delete m;
+      return fail(CSPLOTCH_E_INVALID, "car=1 needs W_sparse or U,V");
+    }
+    for (int i = 0; i < N; ++i) {
+      std::sort(adj0[i].begin(), adj0[i].end());
+      if (d->D_sparse && std::fabs(d->D_sparse[i] - (double)adj0[i].size()) > 0.5) {
+        delete m;
+        return fail(CSPLOTCH_E_INVALID, "D_sparse does not match the adjacency");
+      }
+    }
+  }
+
+  // ---- internal spot order ---------------------------------------------------------------------------
+  // The model is invariant under any relabelling of spots.  The tiled kernel needs every neighbour in the
+  // same or an adjacent tile of kTile spots.  Try the given order first (row-major arrays already satisfy
+  // it); otherwise relabel each connected component breadth-first (Cuthill-McKee), which bounds the
+  // bandwidth by the width of the tissue; if that still does not fit the generic kernel is used.
+  auto fits = [&](const std::vector<int> &perm) {
+    if (!car) return true;
+    std::vector<int> inv(N);
+    for (int j = 0; j < N; ++j) inv[perm[j]] = j;
+    for (int j = 0; j < N; ++j) {
+      const auto &a = adj0[perm[j]];
+      if ((int)a.size() > kMaxEll) return false;
+      for (int nb : a) {
+        const int dt = inv[nb] / kTile - j / kTile;
+        if (dt > 1 || dt < -1) return false;
+      }
+    }
+    return true;
+  };
+  m->perm.resize(N);
+  for (int j = 0; j < N; ++j) m->perm[j] = j;
+  bool tiled = fits(m->perm);
+  const char *force = std::getenv("CSPLOTCH_FORCE_ORDER");  // "cm": always relabel, "generic": never tile (tests)
+  if (car && (!tiled || (force && std::string(force) == "cm"))) {
+    std::vector<int> cm;
+    cm.reserve(N);
+    std::vector<char> seen(N, 0);
+    for (int s0 = 0; s0 < N; ++s0) {
+      if (seen[s0]) continue;
+      // start each component from a far-away node (two BFS sweeps ~ pseudo-peripheral)
+      int start = s0;
+      for (int sweep = 0; sweep < 2; ++sweep) {
+        std::vector<int> q{start};
+        std::vector<char> vis(N, 0);
+        vis[start] = 1;
+        for (size_t h = 0; h < q.size(); ++h)
+          for (int nb : adj0[q[h]])
+            if (!vis[nb]) { vis[nb] = 1; q.push_back(nb); }
+        start = q.back();
+      }
+      std::vector<int> q{start};
+      seen[start] = 1;
+      for (size_t h = 0; h < q.size(); ++h) {
+        std::vector<int> nbs;
+        for (int nb : adj0[q[h]])
+          if (!seen[nb]) { seen[nb] = 1; nbs.push_back(nb); }
+        std::sort(nbs.begin(), nbs.end(), [&](int a, int b) {
+          return adj0[a].size() != adj0[b].size() ? adj0[a].size() < adj0[b].size() : a < b;
+        });
+        q.insert(q.end(), nbs.begin(), nbs.end());
+      }
+      cm.insert(cm.end(), q.begin(), q.end());
+    }
+    if (fits(cm)) { m->perm = cm; tiled = true; }
+  }
+  if (force && std::string(force) == "generic") tiled = false;
+  std::vector<int> inv(N);
+  for (int j = 0; j < N; ++j) inv[m->perm[j]] = j;
+  int ell_w = 0;
+  if (car)
+    for (int i = 0; i < N; ++i) ell_w = std::max(ell_w, (int)adj0[i].size());
+  dm.tiled = tiled ? 1 : 0;
+  dm.ell_w = (car && tiled) ? ell_w : 0;
+  dm.stage_bytes = (5 * kTile) * (int)sizeof(double) + (2 + dm.ell_w) * kTile * (int)sizeof(int);
+  m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 4) * sizeof(double);
+  if (tiled) m->smem_bytes += (size_t)(4 + 2 + 2 + 8) * kTile * sizeof(double) + 2 * (size_t)dm.stage_bytes;
+  if (m->smem_bytes > 220 * 1024) {
     delete m;
     return fail(CSPLOTCH_E_UNSUPPORTED, "beta table (L*C*K) too large for shared memory");
   }
-
-  // spot order: identity for now (the layout supports any permutation)
-  m->perm.resize(N);
-  for (int j = 0; j < N; ++j) m->perm[j] = j;
-  std::vector<int> inv(N);
-  for (int j = 0; j < N; ++j) inv[m->perm[j]] = j;
 
   // Stan offsets (declaration order)
   const int so_psi = 0, so_beta = car ? N : 0, so_scal = so_beta + dm.nbeta, so_noise = so_scal + ns;
@@ -426,8 +546,8 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   for (int s = 0; s < ns; ++s) m->imap[dm.o_small + dm.nbeta + s] = so_scal + s;
 
   // per-spot tables
-  std::vector<double> lsf(N);
-  std::vector<int> key(N);
+  std::vector<double> lsf(dm.Npad, 0.0);
+  std::vector<int> key(dm.Npad, -1);
   {
     std::vector<int> tissue_of(N);
     int j = 0;
@@ -453,37 +573,19 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     map3[i] = d->level_3_mapping[i] - 1;
     if (map3[i] < 0 || map3[i] >= L2) { delete m; return fail(CSPLOTCH_E_INVALID, "level_3_mapping out of range"); }
   }
-  std::vector<int> rowptr(N + 1, 0), col;
+  std::vector<int> rowptr(N + 1, 0), col, ell;
   std::vector<double> eigu, eigm;
   if (car) {
-    if (!d->eig_values) { delete m; return fail(CSPLOTCH_E_INVALID, "car=1 needs eig_values"); }
-    std::vector<std::vector<int>> adj(N);
-    if (d->U && d->V) {
-      for (int i = 0; i < N; ++i)
-        for (int e = d->U[i] - 1; e < d->U[i + 1] - 1; ++e) {
-          const int nb = d->V[e] - 1;
-          if (nb < 0 || nb >= N) { delete m; return fail(CSPLOTCH_E_INVALID, "V out of range"); }
-          adj[inv[i]].push_back(inv[nb]);
-        }
-    } else if (d->W_sparse) {
-      for (int e = 0; e < d->W_n; ++e) {
-        const int a = d->W_sparse[2 * e] - 1, b = d->W_sparse[2 * e + 1] - 1;
-        if (a < 0 || a >= N || b < 0 || b >= N) { delete m; return fail(CSPLOTCH_E_INVALID, "W_sparse out of range"); }
-        adj[inv[a]].push_back(inv[b]);
-        adj[inv[b]].push_back(inv[a]);
-      }
-    } else {
-      delete m;
-      return fail(CSPLOTCH_E_INVALID, "car=1 needs W_sparse or U,V");
-    }
+    if (tiled) ell.assign((size_t)dm.NT * dm.ell_w * kTile, -1);
     for (int i = 0; i < N; ++i) {
-      std::sort(adj[i].begin(), adj[i].end());
-      rowptr[i + 1] = rowptr[i] + (int)adj[i].size();
-      col.insert(col.end(), adj[i].begin(), adj[i].end());
-      if (d->D_sparse && std::fabs(d->D_sparse[m->perm[i]] - (double)adj[i].size()) > 0.5) {
-        delete m;
-        return fail(CSPLOTCH_E_INVALID, "D_sparse does not match the adjacency");
-      }
+      std::vector<int> a;
+      for (int nb : adj0[m->perm[i]]) a.push_back(inv[nb]);
+      std::sort(a.begin(), a.end());
+      rowptr[i + 1] = rowptr[i] + (int)a.size();
+      col.insert(col.end(), a.begin(), a.end());
+      if (tiled)
+        for (size_t w = 0; w < a.size(); ++w)
+          ell[((size_t)(i / kTile) * dm.ell_w + w) * kTile + (i % kTile)] = a[w];
     }
     // distinct eigenvalues with multiplicity (exact duplicates only; c3 has 24 identical arrays)
     std::map<double, double> mult;
@@ -493,17 +595,19 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   }
   std::vector<double> E;
   if (d->family == CSPLOTCH_COMP_SPLOTCH) {
-    E.resize((size_t)N * K);
+    E.assign((size_t)dm.NT * K * kTile, 0.0);
     for (int ji = 0; ji < N; ++ji)
-      for (int k = 0; k < K; ++k) E[(size_t)ji * K + k] = d->E[(size_t)m->perm[ji] * K + k];
+      for (int k = 0; k < K; ++k)
+        E[((size_t)(ji / kTile) * K + k) * kTile + (ji % kTile)] = d->E[(size_t)m->perm[ji] * K + k];
   }
   bool ok = true;
   double *p_lsf, *p_E, *p_eu, *p_em;
-  int *p_key, *p_rp, *p_col, *p_m2, *p_m3, *p_imap;
+  int *p_key, *p_rp, *p_col, *p_m2, *p_m3, *p_imap, *p_ell;
   ok &= m->buf.upload(&p_lsf, lsf) == cudaSuccess;
   ok &= m->buf.upload(&p_key, key) == cudaSuccess;
   ok &= m->buf.upload(&p_rp, rowptr) == cudaSuccess;
   ok &= m->buf.upload(&p_col, col) == cudaSuccess;
+  ok &= m->buf.upload(&p_ell, ell) == cudaSuccess;
   ok &= m->buf.upload(&p_E, E) == cudaSuccess;
   ok &= m->buf.upload(&p_eu, eigu) == cudaSuccess;
   ok &= m->buf.upload(&p_em, eigm) == cudaSuccess;
@@ -515,7 +619,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     delete m;
     return fail(CSPLOTCH_E_CUDA, "model upload failed: " + msg);
   }
-  dm.lsf = p_lsf; dm.key = p_key; dm.rowptr = p_rp; dm.col = p_col; dm.E = p_E; dm.eigu = p_eu; dm.eigm = p_em;
+  dm.lsf = p_lsf; dm.key = p_key; dm.rowptr = p_rp; dm.col = p_col; dm.ell = p_ell; dm.E = p_E; dm.eigu = p_eu; dm.eigm = p_em;
   dm.map2 = p_m2; dm.map3 = p_m3; dm.imap = p_imap;
   *out = m;
   return CSPLOTCH_OK;
@@ -853,6 +957,19 @@ extern "C" int32_t csplotch_sampler_counters(csplotch_sampler *s, int64_t *n_lea
   return CSPLOTCH_OK;
 }
 
+extern "C" int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out6) {
+  if (!s || !out6) return fail(CSPLOTCH_E_INVALID, "null argument");
+  std::vector<ChainScalars> h;
+  int rc = fetch_cs(s, h);
+  if (rc) return rc;
+  for (int i = 0; i < 6; ++i) out6[i] = 0;
+  for (auto &x : h) {
+    out6[0] += x.cyc_eval; out6[1] += x.cyc_merge; out6[2] += x.cyc_copy; out6[3] += x.cyc_other;
+    out6[4] += x.n_merge; out6[5] += x.n_copy;
+  }
+  return CSPLOTCH_OK;
+}
+
 extern "C" int32_t csplotch_sampler_status(csplotch_sampler *s, int32_t *status, int32_t *iters_done) {
   if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
   std::vector<ChainScalars> h;
@@ -948,7 +1065,7 @@ __global__ void __launch_bounds__(kBlock, 2)
 k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm, const double *__restrict__ ps, int G,
               const double *__restrict__ theta_int, const int *__restrict__ gene_of, const int *__restrict__ perm,
               int Bn, double *out, int n_out) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   DevOps<KT> ops(m);
   bind_smem(ops, m, smem);
   ops.jacobian = 0;
@@ -993,8 +1110,8 @@ k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm,
       double ll = 0.0;
       if (KT == 1) ll = bj[0];
       else {
-        const double *Ej = m.E + (size_t)j * m.K;
-        for (int k = 0; k < m.K; ++k) ll += bj[k] * Ej[k];
+        const double *Ej = E_ptr(m, j);
+        for (int k = 0; k < m.K; ++k) ll += bj[k] * Ej[(size_t)k * kTile];
       }
       if (m.car) ll += q[m.o_psi + j];
       ll += sig03 * q[m.o_noise + j];

@@ -25,6 +25,8 @@ namespace csp {
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
 constexpr int kRedMax = 12;  // doubles per block reduction
+constexpr int kTile = kBlock;    // spots per tile of the staged pipeline: thread t <-> spot t of the tile
+constexpr int kMaxEll = 8;       // widest ELL adjacency the tiled path takes (Visium hex: 6, ST / HD grid: 4)
 
 struct DevModel {
   int family, N, Npad, C, K, L1, L2, L3, L, bot0, nbeta, nscal, nsmall, nsmall_pad;
@@ -34,12 +36,17 @@ struct DevModel {
   int o_psi, o_noise, o_small;
   int s_tau, s_a, s_sigma, s_s2, s_s3, s_theta;  // index inside the scalar part, -1 if absent
   int n_eig;
-  int Nc;  // row stride of the counts matrix (int32 elements)
-  const double *lsf;     // [N] log(size_factors)
-  const int *key;        // [N] bottom-level bin: (tissue_mapping[t]-1)*C + D_j-1
+  int Nc;      // row stride of the counts matrix (int32 elements) = Npad
+  int NT;      // tiles of kTile spots; Npad = NT * kTile
+  int tiled;   // 1: every neighbour lies in the same or an adjacent tile and degree <= ell_w
+  int ell_w;   // ELL width (max degree), 0 without CAR
+  int stage_bytes;
+  const double *lsf;     // [Npad] log(size_factors), 0 in the padding
+  const int *key;        // [Npad] bottom-level bin: (tissue_mapping[t]-1)*C + D_j-1, -1 in the padding
   const int *rowptr;     // [N+1] CSR of the symmetric adjacency (internal spot ids)
   const int *col;        // [2 W_n]
-  const double *E;       // [N][K]
+  const int *ell;        // [NT][ell_w][kTile] neighbour spot ids, -1 = none
+  const double *E;       // [NT][K][kTile]  (tile-major, cell type, spot-in-tile): coalesced per k
   const double *eigu;    // [n_eig] distinct eigenvalues
   const double *eigm;    // [n_eig] multiplicities
   const int *map2;       // [L2] 0-based level-1 row of each level-2 row
@@ -97,14 +104,91 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *red) {
   __syncthreads();
 }
 
+
+// ---- sm_100a async-copy plumbing: 1-D bulk copies (TMA engine, SASS UBLKCP) completing on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// E[j][k] in the tile-major layout [NT][K][kTile]
+__device__ __forceinline__ const double *E_ptr(const DevModel &m, int j) {
+  return m.E + ((size_t)(j / kTile) * m.K) * kTile + (j % kTile);
+}
+
+// Sum KP per-lane values over the 32 lanes of a warp with KP/2 + KP/4 + ... + log2(32/KP)+... shuffles
+// (transposed butterfly).  On return v[0] of lane l holds the total of value index bin_of_lane<KP>(l).
+template <int KP>
+__device__ __forceinline__ void warp_transpose_sum(double (&v)[KP]) {
+  const int lane = threadIdx.x & 31;
+  int off = 16;
+#pragma unroll
+  for (int n = KP; n > 1; n >>= 1) {
+    const int half = n >> 1;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < KP / 2; ++i) {
+      if (i < half) {
+        const double send = upper ? v[i] : v[i + half];
+        const double keep = upper ? v[i + half] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    off >>= 1;
+  }
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+template <int KP>
+__device__ __forceinline__ int bin_of_lane(int lane) {
+  // KP = 16: (lane >> 1) & 15; 8: (lane >> 2) & 7; 4: (lane >> 3) & 3; 2: lane >> 4; 1: 0
+  int sh = 0, n = KP;
+  while (n < 32) { n <<= 1; ++sh; }
+  return KP == 1 ? 0 : ((lane >> sh) & (KP - 1));
+}
+template <int KP>
+__device__ __forceinline__ bool lane_owns_bin(int lane) {
+  int sh = 0, n = KP;
+  while (n < 32) { n <<= 1; ++sh; }
+  return (lane & ((1 << sh) - 1)) == 0;
+}
+
 template <int KT>
 struct DevOps {
   const DevModel &m;
   GeneDev gn;
   RngKey key;
   int jacobian;
-  // shared memory: B[nbeta] | adjB[nbeta] | red[kWarps*kRedMax]
+  // shared memory: B[nbeta] | adjB[nbeta] | red[kWarps*kRedMax] | mbar[kStages] | ring[4 T] | phr[2 T] | stages
   double *B, *adjB, *red;
+  uint64_t *mbar;        // "tile landed" barriers: [0,1] psi slots, [2,3] rest slots
+  double *ring;          // drifted psi of tiles k-1, k, k+1 (+1 spare): ring[j & (4 T - 1)]
+  double *phr, *mst;     // half-kicked psi momenta / inverse metric of tiles k, k+1: [(tile & 1) * T + t]
+  double *psi_st;        // 2 slots x {q,p,g,minv}[T] of the psi block (TMA destination)
+  unsigned char *rest_st;  // 2 slots x stage_bytes: {q,p,g,minv}[T] of noise_raw, lsf[T], counts[T], key[T], ell[w][T]
+  uint32_t tile_seq;     // tiles consumed so far by this CTA, mod 4 (slot = seq & 1, parity = (seq >> 1) & 1)
   // HBM vectors of this CTA slot / chain
   double *pool;         // kPoolVecs x Di
   double *zq[2], *zg[2];
@@ -116,7 +200,7 @@ struct DevOps {
   double *out_small;  // [num_samples][nsmall]
   double *out_theta;  // [num_samples][D] Stan order
   double *out_summ;   // [6][N]: mean,M2 of log_lambda | mean,M2 of lambda | mean,M2 of psi
-  long long launches_dummy;
+  long long cyc_eval = 0, cyc_merge = 0, cyc_copy = 0, cyc_other = 0, n_merge = 0, n_copy = 0;
 
   __device__ __forceinline__ DevOps(const DevModel &mm) : m(mm) {}
 
@@ -190,147 +274,13 @@ struct DevOps {
     for (int k = 0; k < KT; ++k) acc[k] = 0.0;
   }
 
-  // ---- fused [half-kick, drift,] log-density + gradient [, half-kick] ------------------------
-  // LEAP: (sq,sg,sp) --eps--> (dq,dg,dp).  !LEAP: dq := sq (if different), dg := -grad lp(sq).
-  // g vectors hold the gradient of the potential V = -lp, like Stan's ps_point::g.
+  // ---- everything after the spot loop: CAR log-determinant, beta prior, block reductions, reverse of
+  // the hierarchy, gradients (and second half-kick) of the small block, scalar chain rule --------------
   template <bool LEAP>
-  __device__ void eval(const double *sq, const double *sg, const double *sp, double *dq, double *dg,
-                       double *dp, double eps, double *V_out, double *K_out, bool *finite_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int Di = m.Di;
-    // phase A: half-kick + drift for every element (the spot loop below gathers psi of
-    // neighbours, so all of psi must have moved before any gradient is taken)
-    if (LEAP) {
-      for (int e = 2 * tid; e < Di; e += 2 * kBlock) {
-        const double2 q = *reinterpret_cast<const double2 *>(sq + e);
-        const double2 g = *reinterpret_cast<const double2 *>(sg + e);
-        const double2 p = *reinterpret_cast<const double2 *>(sp + e);
-        const double2 mi = *reinterpret_cast<const double2 *>(minv + e);
-        double2 ph, qn;
-        ph.x = p.x - 0.5 * eps * g.x;
-        ph.y = p.y - 0.5 * eps * g.y;
-        qn.x = q.x + eps * mi.x * ph.x;
-        qn.y = q.y + eps * mi.y * ph.y;
-        *reinterpret_cast<double2 *>(dq + e) = qn;
-        *reinterpret_cast<double2 *>(dp + e) = ph;
-      }
-    } else if (dq != sq) {
-      for (int e = 2 * tid; e < Di; e += 2 * kBlock)
-        *reinterpret_cast<double2 *>(dq + e) = *reinterpret_cast<const double2 *>(sq + e);
-    }
-    __syncthreads();
-
-    Scalars sc;
-    load_small(dq, sc);
-    for (int idx = tid; idx < m.nbeta; idx += kBlock) adjB[idx] = 0.0;
-    __syncthreads();
-
-    const double heads = m.zi ? log(sc.theta) : 0.0;
-    const double tails = m.zi ? log1p(-sc.theta) : 0.0;
-    const double sig03 = 0.3 * sc.sigma;
-    const double *psi = dq + m.o_psi;
-    const double *noi = dq + m.o_noise;
-    double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0;
-    double acc[KT];
-#pragma unroll
-    for (int k = 0; k < KT; ++k) acc[k] = 0.0;
-    int cur_key = -1;
-
-    // each warp owns a contiguous chunk of spots, 32 consecutive spots per trip
-    const int chunk = (((m.N + kWarps - 1) / kWarps) + 31) & ~31;
-    const int j_end = min(m.N, (warp + 1) * chunk);
-    for (int base = warp * chunk; base < j_end; base += 32) {
-      const int j = base + lane;
-      const bool act = j < j_end;
-      int kj = -1;
-      double gj = 0.0;
-      double e[KT];
-      if (act) {
-        kj = m.key[j];
-        const double eps_j = noi[j];
-        double ll;
-        const double *bj = B + (m.bot0 * m.C) * m.K + kj * m.K;
-        if (KT == 1) {
-          ll = bj[0];
-          e[0] = 1.0;
-        } else {
-          ll = 0.0;
-          const double *Ej = m.E + (size_t)j * m.K;
-#pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            e[k] = (k < m.K) ? Ej[k] : 0.0;
-            if (k < m.K) ll += bj[k] * e[k];
-          }
-        }
-        double psi_j = 0.0, Wpsi = 0.0, deg = 0.0;
-        if (m.car) {
-          psi_j = psi[j];
-          const int r0 = m.rowptr[j], r1 = m.rowptr[j + 1];
-          for (int r = r0; r < r1; ++r) Wpsi += psi[m.col[r]];
-          deg = (double)(r1 - r0);
-          ll += psi_j;
-        }
-        ll += sig03 * eps_j;
-        const double eta = ll + m.lsf[j];
-        const double mu = exp(eta);
-        const int y = gn.counts[j];
-        if (m.zi && y == 0) {
-          // log_sum_exp(log theta, log1m theta - mu) and its softmax weights
-          const double Bq = tails - mu;
-          const double dd = heads - Bq;
-          const double t = exp(-fabs(dd));
-          const double l1p = log1p(t);
-          const double wmax = 1.0 / (1.0 + t), wmin = t / (1.0 + t);
-          const double wA = dd >= 0 ? wmax : wmin;
-          const double wB = dd >= 0 ? wmin : wmax;
-          a_lp += (dd >= 0 ? heads : Bq) + l1p;
-          gj = -wB * mu;
-          a_dth += wA / sc.theta - wB / (1.0 - sc.theta);
-        } else {
-          a_lp += (double)y * eta - mu;
-          gj = (double)y - mu;
-        }
-        a_lp -= 0.5 * eps_j * eps_j;
-        a_ng += eps_j * gj;
-        const double gr_eps = sig03 * gj - eps_j;
-        dg[m.o_noise + j] = -gr_eps;
-        a_g2 += gr_eps * gr_eps;
-        if (LEAP) {
-          const double pn = dp[m.o_noise + j] + 0.5 * eps * gr_eps;
-          dp[m.o_noise + j] = pn;
-          a_kin += minv[m.o_noise + j] * pn * pn;
-        }
-        if (m.car) {
-          a_qD += (psi_j * deg) * psi_j;
-          a_qW += Wpsi * psi_j;
-          const double gr_psi = gj - sc.tau * (deg * psi_j - sc.a * Wpsi);
-          dg[m.o_psi + j] = -gr_psi;
-          a_g2 += gr_psi * gr_psi;
-          if (LEAP) {
-            const double pn = dp[m.o_psi + j] + 0.5 * eps * gr_psi;
-            dp[m.o_psi + j] = pn;
-            a_kin += minv[m.o_psi + j] * pn * pn;
-          }
-        }
-      }
-      // bottom-level bins: per-lane run-length accumulation, warp-collective flush on change
-      const bool changed = act && (kj != cur_key) && (cur_key >= 0);
-      if (__any_sync(0xffffffffu, changed)) flush_bins(acc, cur_key);
-      if (act) {
-        cur_key = kj;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) acc[k] += gj * e[k];
-      }
-    }
-    flush_bins(acc, cur_key);
-
-    // padding elements (Npad > N) carry q = p = g = 0
-    if (m.Npad > m.N && tid == 0) {
-      dg[m.o_noise + m.N] = 0.0;
-      if (LEAP) dp[m.o_noise + m.N] = 0.0;
-      if (m.car) { dg[m.o_psi + m.N] = 0.0; if (LEAP) dp[m.o_psi + m.N] = 0.0; }
-    }
-
+  __device__ void finish(const Scalars &sc, double a_lp, double a_ng, double a_qD, double a_qW, double a_dth,
+                         double a_kin, double a_g2, double tails, double *dq, double *dg, double *dp, double eps,
+                         double *V_out, double *K_out, bool *finite_out) {
+    const int tid = threadIdx.x;
     // log-determinant term of the CAR prior over the distinct eigenvalues
     double a_ldet = 0, a_dldet = 0;
     if (m.car) {
@@ -449,8 +399,447 @@ struct DevOps {
     if (finite_out) *finite_out = isfinite(lp) && isfinite(g2);
   }
 
+
+  // ---- tiled pipeline (the fast path) -----------------------------------------------------------------
+  // (__noinline__: the sampler's control state must not compete for registers with this loop; inlined into
+  //  the persistent kernel ptxas spilled ~1 kB per thread inside the spot loop)
+  // Tile k = spots [k T, (k+1) T), thread t <-> spot k T + t.  One elected thread streams every per-spot
+  // input of tile k+2 into shared memory with 1-D TMA bulk copies while the CTA (i) drifts psi of tile k+1
+  // into a 4-tile ring and (ii) evaluates likelihood + CAR + gradient + second half-kick of tile k reading
+  // neighbours from the ring.  HBM traffic per leapfrog = the algorithmic 56 D + 4 N bytes (+ gene-shared
+  // tables from L2); one __syncthreads per tile.
+  // Everything the tile loop touches, hoisted into registers once per call: the object itself lives in
+  // local memory (the functions are __noinline__), so member / model-field accesses inside the loop would
+  // be dependent generic loads on the critical path.
+  struct TileCtx {
+    int NT, K, ell_w, car, zi, o_psi, o_noise, stage_bytes, bin0;
+    uint32_t seq0;
+    const double *E, *lsf_g, *minv_g;
+    const int *key_g, *ell_g, *cnt_g;
+    double *ring, *phr, *mst, *psi_st, *Bbot, *adjB;
+    unsigned char *rest_st;
+    uint64_t *mbar;
+  };
+  __device__ __forceinline__ TileCtx make_ctx() const {
+    TileCtx c;
+    c.NT = m.NT; c.K = m.K; c.ell_w = m.ell_w; c.car = m.car; c.zi = m.zi;
+    c.o_psi = m.o_psi; c.o_noise = m.o_noise; c.stage_bytes = m.stage_bytes;
+    c.bin0 = (m.bot0 * m.C) * m.K;
+    c.seq0 = tile_seq;
+    c.E = m.E; c.lsf_g = m.lsf; c.minv_g = minv; c.key_g = m.key; c.ell_g = m.ell; c.cnt_g = gn.counts;
+    c.ring = ring; c.phr = phr; c.mst = mst; c.psi_st = psi_st; c.Bbot = B + c.bin0; c.adjB = adjB;
+    c.rest_st = rest_st; c.mbar = mbar;
+    return c;
+  }
+  // Both pipelines are two slots deep: tile k lives in slot (seq0 + k) & 1 and (seq0 + k) >> 1 counts its
+  // uses.  psi inputs run two tiles ahead (the drift of tile k+1 precedes the gradient of tile k), the rest one.
+  template <bool LEAP>
+  static __device__ __forceinline__ void issue_psi(const TileCtx &c, int k, const double *sq, const double *sg,
+                                                   const double *sp) {
+    const uint32_t seq = c.seq0 + (uint32_t)k;
+    uint64_t *bar = c.mbar + (seq & 1u);
+    double *d = c.psi_st + (size_t)(seq & 1u) * 4 * kTile;
+    const size_t off = (size_t)c.o_psi + (size_t)k * kTile;
+    constexpr uint32_t vb = kTile * sizeof(double);
+    mbar_expect_tx(bar, LEAP ? 4 * vb : vb);
+    bulk_g2s(d, sq + off, vb, bar);
+    if (LEAP) {
+      bulk_g2s(d + kTile, sp + off, vb, bar);
+      bulk_g2s(d + 2 * kTile, sg + off, vb, bar);
+      bulk_g2s(d + 3 * kTile, c.minv_g + off, vb, bar);
+    }
+  }
+  template <bool LEAP>
+  static __device__ __forceinline__ void issue_rest(const TileCtx &c, int k, const double *sq, const double *sg,
+                                                    const double *sp) {
+    const uint32_t seq = c.seq0 + (uint32_t)k;
+    uint64_t *bar = c.mbar + 2 + (seq & 1u);
+    double *d = reinterpret_cast<double *>(c.rest_st + (size_t)(seq & 1u) * c.stage_bytes);
+    int *ip = reinterpret_cast<int *>(d + 5 * kTile);
+    const size_t toff = (size_t)k * kTile, off = (size_t)c.o_noise + toff;
+    constexpr uint32_t vb = kTile * sizeof(double), ib = kTile * sizeof(int);
+    mbar_expect_tx(bar, (LEAP ? 4 * vb : vb) + vb + 2 * ib + (c.car ? (uint32_t)c.ell_w * ib : 0u));
+    bulk_g2s(d, sq + off, vb, bar);
+    if (LEAP) {
+      bulk_g2s(d + kTile, sp + off, vb, bar);
+      bulk_g2s(d + 2 * kTile, sg + off, vb, bar);
+      bulk_g2s(d + 3 * kTile, c.minv_g + off, vb, bar);
+    }
+    bulk_g2s(d + 4 * kTile, c.lsf_g + toff, vb, bar);
+    bulk_g2s(ip, c.cnt_g + toff, ib, bar);
+    bulk_g2s(ip + kTile, c.key_g + toff, ib, bar);
+    if (c.car) bulk_g2s(ip + 2 * kTile, c.ell_g + (size_t)k * c.ell_w * kTile, (uint32_t)c.ell_w * ib, bar);
+  }
+  // drift psi of tile k into the ring; keep the half-kicked momentum and the metric for the gradient phase
+  template <bool LEAP>
+  static __device__ __forceinline__ void drift_tile(const TileCtx &c, int k, double eps) {
+    const int t = threadIdx.x;
+    const uint32_t seq = c.seq0 + (uint32_t)k;
+    mbar_wait(c.mbar + (seq & 1u), (seq >> 1) & 1u);
+    const double *d = c.psi_st + (size_t)(seq & 1u) * 4 * kTile;
+    double qn = d[t];
+    if (LEAP) {
+      const double mi = d[3 * kTile + t];
+      const double ph = d[kTile + t] - 0.5 * eps * d[2 * kTile + t];
+      qn += eps * mi * ph;
+      c.phr[(k & 1) * kTile + t] = ph;
+      c.mst[(k & 1) * kTile + t] = mi;
+    }
+    c.ring[((k & 3) * kTile) + t] = qn;
+  }
+
+  // per-tile contribution of one warp to the bottom-level bins: G[key][k] += sum_lanes gj * E[lane][k]
+  template <int KP>
+  static __device__ __forceinline__ void add_bins(double *bins, int K, double (&v)[KP], int key_l) {
+    const int lane = threadIdx.x & 31;
+    const int k0 = __shfl_sync(0xffffffffu, key_l, 0);
+    if (__all_sync(0xffffffffu, key_l == k0)) {
+      if (k0 < 0) return;
+      warp_transpose_sum<KP>(v);
+      const int b = bin_of_lane<KP>(lane);
+      if (lane_owns_bin<KP>(lane) && b < K) atomicAdd(&bins[k0 * K + b], v[0]);
+      return;
+    }
+    unsigned remaining = __ballot_sync(0xffffffffu, key_l >= 0);
+    while (remaining) {
+      const int leader = __ffs(remaining) - 1;
+      const int kk = __shfl_sync(0xffffffffu, key_l, leader);
+      const bool mine = key_l == kk;
+      double w[KP];
+#pragma unroll
+      for (int i = 0; i < KP; ++i) w[i] = mine ? v[i] : 0.0;
+      warp_transpose_sum<KP>(w);
+      const int b = bin_of_lane<KP>(lane);
+      if (lane_owns_bin<KP>(lane) && b < K) atomicAdd(&bins[kk * K + b], w[0]);
+      remaining &= ~__ballot_sync(0xffffffffu, mine);
+    }
+  }
+
+  template <bool LEAP>
+  __device__ __noinline__ void eval_tiled(const double *__restrict__ sq, const double *__restrict__ sg,
+                                          const double *__restrict__ sp, double *dq, double *dg, double *dp,
+                                          double eps, double *V_out, double *K_out, bool *finite_out) {
+    constexpr int KP = KT <= 1 ? 1 : (KT <= 4 ? 4 : (KT <= 8 ? 8 : 16));
+    const int tid = threadIdx.x;
+    const TileCtx c = make_ctx();
+    const int NT = c.NT;
+    const bool write_q = LEAP || dq != sq;
+    // generic-proxy writes of earlier passes (q, p, g of this chain) must be visible to the async proxy
+    // (TMA) that is about to read them
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    // the first tiles start streaming while the small block is prepared
+    if (tid == 0) {
+      if (c.car) {
+        issue_psi<LEAP>(c, 0, sq, sg, sp);
+        if (NT > 1) issue_psi<LEAP>(c, 1, sq, sg, sp);
+      }
+      issue_rest<LEAP>(c, 0, sq, sg, sp);
+    }
+    // small block: half-kick + drift (or copy), then constrained scalars and beta levels
+    for (int e = m.o_small + tid; e < m.Di; e += kBlock) {
+      double qn = sq[e];
+      if (LEAP) {
+        const double ph = sp[e] - 0.5 * eps * sg[e];
+        qn += eps * minv[e] * ph;
+        dp[e] = ph;
+      }
+      if (write_q) dq[e] = qn;
+    }
+    __syncthreads();
+    Scalars sc;
+    load_small(dq, sc);
+    for (int idx = tid; idx < m.nbeta; idx += kBlock) adjB[idx] = 0.0;
+    const double heads = c.zi ? log(sc.theta) : 0.0;
+    const double tails = c.zi ? log1p(-sc.theta) : 0.0;
+    const double sig03 = 0.3 * sc.sigma;
+    const double theta = sc.theta, tau = sc.tau, a_car = sc.a;
+    const double inv_theta = c.zi ? 1.0 / theta : 0.0, inv_1mtheta = c.zi ? 1.0 / (1.0 - theta) : 0.0;
+    double *const dq_psi = dq + c.o_psi, *const dq_eps = dq + c.o_noise;
+    double *const dg_psi = dg + c.o_psi, *const dg_eps = dg + c.o_noise;
+    double *const dp_psi = dp + c.o_psi, *const dp_eps = dp + c.o_noise;
+    double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0;
+
+    if (c.car) drift_tile<LEAP>(c, 0, eps);
+    for (int k = 0; k < NT; ++k) {
+      // cell-type fractions of this tile straight from L2 (gene-shared, coalesced per k); issued before
+      // the barrier so that their latency overlaps the drift of the next tile and the barrier wait
+      double e[KT];
+      if (KT > 1) {
+        const double *Ej = c.E + ((size_t)k * c.K) * kTile + tid;
+#pragma unroll
+        for (int i = 0; i < KT; ++i) e[i] = (i < c.K) ? __ldg(Ej + (size_t)i * kTile) : 0.0;
+      } else {
+        e[0] = 1.0;
+      }
+      if (c.car && k + 1 < NT) drift_tile<LEAP>(c, k + 1, eps);
+      __syncthreads();  // ring(k+1) complete; every thread is done with the gradient of tile k-1
+      if (tid == 0) {
+        if (c.car && k + 2 < NT) issue_psi<LEAP>(c, k + 2, sq, sg, sp);  // slot of tile k: drifted one trip ago
+        if (k + 1 < NT) issue_rest<LEAP>(c, k + 1, sq, sg, sp);          // slot of tile k-1
+      }
+      const uint32_t seq = c.seq0 + (uint32_t)k;
+      mbar_wait(c.mbar + 2 + (seq & 1u), (seq >> 1) & 1u);
+      const double *rd = reinterpret_cast<const double *>(c.rest_st + (size_t)(seq & 1u) * c.stage_bytes);
+      const int *ri = reinterpret_cast<const int *>(rd + 5 * kTile);
+      const int j = k * kTile + tid;
+      const int kj = ri[kTile + tid];  // -1 in the padding
+      double gj = 0.0;
+      double ge[KP];
+#pragma unroll
+      for (int i = 0; i < KP; ++i) ge[i] = 0.0;
+      if (kj >= 0) {
+        // noise_raw: drift in registers
+        double eps_j = rd[tid], ph_e = 0.0, m_e = 0.0;
+        if (LEAP) {
+          m_e = rd[3 * kTile + tid];
+          ph_e = rd[kTile + tid] - 0.5 * eps * rd[2 * kTile + tid];
+          eps_j += eps * m_e * ph_e;
+        }
+        const double *bj = c.Bbot + kj * c.K;
+        double ll;
+        if (KT == 1) {
+          ll = bj[0];
+        } else {
+          ll = 0.0;
+#pragma unroll
+          for (int i = 0; i < KT; ++i)
+            if (i < c.K) ll += bj[i] * e[i];
+        }
+        double psi_j = 0.0, Wpsi = 0.0, deg = 0.0;
+        if (c.car) {
+          psi_j = c.ring[j & (4 * kTile - 1)];
+          const int *el = ri + 2 * kTile + tid;
+#pragma unroll
+          for (int w = 0; w < kMaxEll; ++w) {
+            if (w < c.ell_w) {
+              const int nb = el[w * kTile];
+              if (nb >= 0) {
+                Wpsi += c.ring[nb & (4 * kTile - 1)];
+                deg += 1.0;
+              }
+            }
+          }
+          ll += psi_j;
+        }
+        ll += sig03 * eps_j;
+        const double eta = ll + rd[4 * kTile + tid];
+        const double mu = exp(eta);
+        const int y = ri[tid];
+        if (c.zi && y == 0) {
+          const double Bq = tails - mu;
+          const double dd = heads - Bq;
+          const double tt = exp(-fabs(dd));
+          const double l1p = log1p(tt);
+          const double wmax = 1.0 / (1.0 + tt), wmin = tt * wmax;
+          const double wA = dd >= 0 ? wmax : wmin;
+          const double wB = dd >= 0 ? wmin : wmax;
+          a_lp += (dd >= 0 ? heads : Bq) + l1p;
+          gj = -wB * mu;
+          a_dth += wA * inv_theta - wB * inv_1mtheta;
+        } else {
+          a_lp += (double)y * eta - mu;
+          gj = (double)y - mu;
+        }
+        a_lp -= 0.5 * eps_j * eps_j;
+        a_ng += eps_j * gj;
+        const double gr_eps = sig03 * gj - eps_j;
+        a_g2 += gr_eps * gr_eps;
+        dg_eps[j] = -gr_eps;
+        if (write_q) dq_eps[j] = eps_j;
+        if (LEAP) {
+          const double pn = ph_e + 0.5 * eps * gr_eps;
+          dp_eps[j] = pn;
+          a_kin += m_e * pn * pn;
+        }
+        if (c.car) {
+          a_qD += (psi_j * deg) * psi_j;
+          a_qW += Wpsi * psi_j;
+          const double gr_psi = gj - tau * (deg * psi_j - a_car * Wpsi);
+          a_g2 += gr_psi * gr_psi;
+          dg_psi[j] = -gr_psi;
+          if (write_q) dq_psi[j] = psi_j;
+          if (LEAP) {
+            const double pn = c.phr[(k & 1) * kTile + tid] + 0.5 * eps * gr_psi;
+            dp_psi[j] = pn;
+            a_kin += c.mst[(k & 1) * kTile + tid] * pn * pn;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < KT; ++i) ge[i] = gj * e[i];
+      } else {
+        // padding spots carry q = p = g = 0
+        dg_eps[j] = 0.0;
+        if (write_q) dq_eps[j] = 0.0;
+        if (LEAP) dp_eps[j] = 0.0;
+        if (c.car) {
+          dg_psi[j] = 0.0;
+          if (write_q) dq_psi[j] = 0.0;
+          if (LEAP) dp_psi[j] = 0.0;
+        }
+      }
+      add_bins<KP>(c.adjB + c.bin0, c.K, ge, kj);
+    }
+    tile_seq = (c.seq0 + (uint32_t)NT) & 3u;
+    finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out);
+  }
+
+  // ---- fused [half-kick, drift,] log-density + gradient [, half-kick] ------------------------
+  // LEAP: (sq,sg,sp) --eps--> (dq,dg,dp).  !LEAP: dq := sq (if different), dg := -grad lp(sq).
+  // g vectors hold the gradient of the potential V = -lp, like Stan's ps_point::g.
+  template <bool LEAP>
+  __device__ void eval(const double *sq, const double *sg, const double *sp, double *dq, double *dg,
+                       double *dp, double eps, double *V_out, double *K_out, bool *finite_out) {
+    if (m.tiled) eval_tiled<LEAP>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out);
+    else eval_generic<LEAP>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out);
+  }
+
+  // Fallback for layouts the tiled pipeline does not take (neighbours further than one tile away or
+  // degree > kMaxEll): two phases through HBM/L2 with a CSR gather.
+  template <bool LEAP>
+  __device__ __noinline__ void eval_generic(const double *sq, const double *sg, const double *sp, double *dq, double *dg,
+                               double *dp, double eps, double *V_out, double *K_out, bool *finite_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Di = m.Di;
+    // phase A: half-kick + drift for every element (the spot loop below gathers psi of
+    // neighbours, so all of psi must have moved before any gradient is taken)
+    if (LEAP) {
+      for (int e = 2 * tid; e < Di; e += 2 * kBlock) {
+        const double2 q = *reinterpret_cast<const double2 *>(sq + e);
+        const double2 g = *reinterpret_cast<const double2 *>(sg + e);
+        const double2 p = *reinterpret_cast<const double2 *>(sp + e);
+        const double2 mi = *reinterpret_cast<const double2 *>(minv + e);
+        double2 ph, qn;
+        ph.x = p.x - 0.5 * eps * g.x;
+        ph.y = p.y - 0.5 * eps * g.y;
+        qn.x = q.x + eps * mi.x * ph.x;
+        qn.y = q.y + eps * mi.y * ph.y;
+        *reinterpret_cast<double2 *>(dq + e) = qn;
+        *reinterpret_cast<double2 *>(dp + e) = ph;
+      }
+    } else if (dq != sq) {
+      for (int e = 2 * tid; e < Di; e += 2 * kBlock)
+        *reinterpret_cast<double2 *>(dq + e) = *reinterpret_cast<const double2 *>(sq + e);
+    }
+    __syncthreads();
+
+    Scalars sc;
+    load_small(dq, sc);
+    for (int idx = tid; idx < m.nbeta; idx += kBlock) adjB[idx] = 0.0;
+    __syncthreads();
+
+    const double heads = m.zi ? log(sc.theta) : 0.0;
+    const double tails = m.zi ? log1p(-sc.theta) : 0.0;
+    const double sig03 = 0.3 * sc.sigma;
+    const double *psi = dq + m.o_psi;
+    const double *noi = dq + m.o_noise;
+    double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0;
+    double acc[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) acc[k] = 0.0;
+    int cur_key = -1;
+
+    // each warp owns a contiguous chunk of spots, 32 consecutive spots per trip
+    const int chunk = (((m.N + kWarps - 1) / kWarps) + 31) & ~31;
+    const int j_end = min(m.N, (warp + 1) * chunk);
+    for (int base = warp * chunk; base < j_end; base += 32) {
+      const int j = base + lane;
+      const bool act = j < j_end;
+      int kj = -1;
+      double gj = 0.0;
+      double e[KT];
+      if (act) {
+        kj = m.key[j];
+        const double eps_j = noi[j];
+        double ll;
+        const double *bj = B + (m.bot0 * m.C) * m.K + kj * m.K;
+        if (KT == 1) {
+          ll = bj[0];
+          e[0] = 1.0;
+        } else {
+          ll = 0.0;
+          const double *Ej = E_ptr(m, j);
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            e[k] = (k < m.K) ? Ej[(size_t)k * kTile] : 0.0;
+            if (k < m.K) ll += bj[k] * e[k];
+          }
+        }
+        double psi_j = 0.0, Wpsi = 0.0, deg = 0.0;
+        if (m.car) {
+          psi_j = psi[j];
+          const int r0 = m.rowptr[j], r1 = m.rowptr[j + 1];
+          for (int r = r0; r < r1; ++r) Wpsi += psi[m.col[r]];
+          deg = (double)(r1 - r0);
+          ll += psi_j;
+        }
+        ll += sig03 * eps_j;
+        const double eta = ll + m.lsf[j];
+        const double mu = exp(eta);
+        const int y = gn.counts[j];
+        if (m.zi && y == 0) {
+          // log_sum_exp(log theta, log1m theta - mu) and its softmax weights
+          const double Bq = tails - mu;
+          const double dd = heads - Bq;
+          const double t = exp(-fabs(dd));
+          const double l1p = log1p(t);
+          const double wmax = 1.0 / (1.0 + t), wmin = t / (1.0 + t);
+          const double wA = dd >= 0 ? wmax : wmin;
+          const double wB = dd >= 0 ? wmin : wmax;
+          a_lp += (dd >= 0 ? heads : Bq) + l1p;
+          gj = -wB * mu;
+          a_dth += wA / sc.theta - wB / (1.0 - sc.theta);
+        } else {
+          a_lp += (double)y * eta - mu;
+          gj = (double)y - mu;
+        }
+        a_lp -= 0.5 * eps_j * eps_j;
+        a_ng += eps_j * gj;
+        const double gr_eps = sig03 * gj - eps_j;
+        dg[m.o_noise + j] = -gr_eps;
+        a_g2 += gr_eps * gr_eps;
+        if (LEAP) {
+          const double pn = dp[m.o_noise + j] + 0.5 * eps * gr_eps;
+          dp[m.o_noise + j] = pn;
+          a_kin += minv[m.o_noise + j] * pn * pn;
+        }
+        if (m.car) {
+          a_qD += (psi_j * deg) * psi_j;
+          a_qW += Wpsi * psi_j;
+          const double gr_psi = gj - sc.tau * (deg * psi_j - sc.a * Wpsi);
+          dg[m.o_psi + j] = -gr_psi;
+          a_g2 += gr_psi * gr_psi;
+          if (LEAP) {
+            const double pn = dp[m.o_psi + j] + 0.5 * eps * gr_psi;
+            dp[m.o_psi + j] = pn;
+            a_kin += minv[m.o_psi + j] * pn * pn;
+          }
+        }
+      }
+      // bottom-level bins: per-lane run-length accumulation, warp-collective flush on change
+      const bool changed = act && (kj != cur_key) && (cur_key >= 0);
+      if (__any_sync(0xffffffffu, changed)) flush_bins(acc, cur_key);
+      if (act) {
+        cur_key = kj;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[k] += gj * e[k];
+      }
+    }
+    flush_bins(acc, cur_key);
+
+    // padding elements (Npad > N) carry q = p = g = 0
+    for (int j = m.N + tid; j < m.Npad; j += kBlock) {
+      dg[m.o_noise + j] = 0.0;
+      if (LEAP) dp[m.o_noise + j] = 0.0;
+      if (m.car) { dg[m.o_psi + j] = 0.0; if (LEAP) dp[m.o_psi + j] = 0.0; }
+    }
+
+    finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out);
+  }
+
   // ---- Ops interface of nuts_core.h ---------------------------------------------------------------
-  __device__ double sample_momentum(int pv, uint32_t purpose, uint32_t sub, uint32_t iter) {
+  __device__ __noinline__ double sample_momentum(int pv, uint32_t purpose, uint32_t sub, uint32_t iter) {
+    const long long t0 = clock64();
     double *p = vec(pv);
     double k = 0.0;
     for (int e = threadIdx.x; e < m.Di; e += kBlock) {
@@ -466,19 +855,31 @@ struct DevOps {
     double r[1] = {k};
     block_sum<1>(r, red);
     sample_is_q0 = true;
+    cyc_other += clock64() - t0;
     return 0.5 * r[0];
   }
   __device__ double eval_at_current(int z, bool *finite) {
     double V;
+    const long long t0 = clock64();
     eval<false>(q_cur, nullptr, nullptr, zq[z], zg[z], nullptr, 0.0, &V, nullptr, finite);
+    cyc_eval += clock64() - t0;
     return V;
   }
   __device__ void leapfrog(int zs, int ps, int zd, int pd, double eps, double *V, double *K) {
+    const long long t0 = clock64();
     eval<true>(zq[zs], zg[zs], vec(ps), zq[zd], zg[zd], vec(pd), eps, V, K, nullptr);
+    cyc_eval += clock64() - t0;
   }
   // Stan's three generalised U-turn criteria for the subtree L ++ C (base_nuts.hpp
   // build_tree / transition) as six metric-weighted inner products in one pass.
   __device__ bool merge(SubTree L, SubTree C, int rho_out) {
+    const long long t0 = clock64();
+    const bool r = merge_pass(L, C, rho_out);
+    cyc_merge += clock64() - t0;
+    ++n_merge;
+    return r;
+  }
+  __device__ __noinline__ bool merge_pass(SubTree L, SubTree C, int rho_out) {
     const double *Lpb = vec(L.pb), *Lpe = vec(L.pe), *Lrho = vec(L.rho);
     const double *Cpb = vec(C.pb), *Cpe = vec(C.pe), *Crho = vec(C.rho);
     double *out = vec(rho_out);
@@ -508,12 +909,17 @@ struct DevOps {
     block_sum<6>(r, red);
     return (r[1] > 0 && r[0] > 0) && (r[3] > 0 && r[2] > 0) && (r[5] > 0 && r[4] > 0);
   }
-  __device__ void copy_vec(double *dst, const double *src) {
+  __device__ __noinline__ void copy_vec(double *dst, const double *src) {
     for (int e = 2 * threadIdx.x; e < m.Di; e += 2 * kBlock)
       *reinterpret_cast<double2 *>(dst + e) = *reinterpret_cast<const double2 *>(src + e);
     __syncthreads();
   }
-  __device__ void copy_q_to_prop(int z) { copy_vec(q_prop, zq[z]); }
+  __device__ void copy_q_to_prop(int z) {
+    const long long t0 = clock64();
+    copy_vec(q_prop, zq[z]);
+    cyc_copy += clock64() - t0;
+    ++n_copy;
+  }
   __device__ void swap_prop_sample() {
     double *t = q_prop;
     q_prop = q_samp;
@@ -521,20 +927,22 @@ struct DevOps {
     sample_is_q0 = false;
   }
   __device__ void commit_sample() {
+    const long long t0 = clock64();
     if (!sample_is_q0) copy_vec(q_cur, q_samp);
+    cyc_copy += clock64() - t0;
   }
-  __device__ void init_uniform(uint32_t attempt, double radius) {
+  __device__ __noinline__ void init_uniform(uint32_t attempt, double radius) {
     for (int e = threadIdx.x; e < m.Di; e += kBlock) {
       const int si = m.imap[e];
       q_cur[e] = si >= 0 ? rng_init(key, attempt, (uint32_t)si, radius) : 0.0;
     }
     __syncthreads();
   }
-  __device__ void set_unit_metric() {
+  __device__ __noinline__ void set_unit_metric() {
     for (int e = threadIdx.x; e < m.Di; e += kBlock) { minv[e] = 1.0; wm[e] = 0.0; wm2[e] = 0.0; }
     __syncthreads();
   }
-  __device__ void welford_add(double n) {
+  __device__ __noinline__ void welford_add(double n) {
     for (int e = threadIdx.x; e < m.Di; e += kBlock) {
       const double q = q_cur[e];
       const double delta = q - wm[e];
@@ -544,7 +952,7 @@ struct DevOps {
     }
     __syncthreads();
   }
-  __device__ void metric_update(double n) {
+  __device__ __noinline__ void metric_update(double n) {
     for (int e = threadIdx.x; e < m.Di; e += kBlock) {
       double v = minv[e];
       if (n > 1) v = wm2[e] / (n - 1.0);
@@ -556,7 +964,7 @@ struct DevOps {
   }
   // one sampling draw: sampler columns, the small block, optional full theta, and the streaming
   // summaries summarize_stan_hdf5 needs (/root/reference/splotch/utils.py:234-257)
-  __device__ void record_draw(const DrawInfo &info, int s) {
+  __device__ __noinline__ void record_draw(const DrawInfo &info, int s) {
     const int tid = threadIdx.x;
     if (out_diag && tid == 0) {
       double *r = out_diag + (size_t)s * 7;
@@ -585,8 +993,8 @@ struct DevOps {
           ll = bj[0];
         } else {
           ll = 0.0;
-          const double *Ej = m.E + (size_t)j * m.K;
-          for (int k = 0; k < m.K; ++k) ll += bj[k] * Ej[k];
+          const double *Ej = E_ptr(m, j);
+          for (int k = 0; k < m.K; ++k) ll += bj[k] * Ej[(size_t)k * kTile];
         }
         double psi_j = 0.0;
         if (m.car) { psi_j = q_cur[m.o_psi + j]; ll += psi_j; }

@@ -52,6 +52,8 @@ struct ChainScalars {
   double wel_n;
   long long n_leapfrog_total;  // sum of n_leapfrog__ over transitions
   long long n_grad_total;      // every gradient evaluation actually performed
+  // device-side profile (SM clock cycles of this chain's CTA spent inside each collective op)
+  long long cyc_eval, cyc_merge, cyc_copy, cyc_other, n_merge, n_copy;
 };
 
 struct DrawInfo {

@@ -107,6 +107,77 @@ def test_lp_grad_matches_oracle_config_shapes(name):
     assert _rel(grad, g0) < 1e-10
 
 
+def _shuffled_grid_design(seed, family, side=30, n_arrays=2):
+    """Two side x side arrays whose spots are listed in random order: the given order does not tile
+    (neighbours up to ~N apart), the breadth-first relabelling inside csplotch_model_create does."""
+    rng = np.random.default_rng(seed)
+    sizes, pairs, eigs = [], [], []
+    for _ in range(n_arrays):
+        n = side * side
+        perm = rng.permutation(n)
+        p = np.sort(perm[synth.grid4_pairs(side, side)], axis=1)
+        p = p[np.lexsort((p[:, 1], p[:, 0]))]
+        sizes.append(n); pairs.append(p); eigs.append(synth.car_eigenvalues(p, n))
+    N = sum(sizes)
+    C, K = 5, 4
+    E = synth.scale_and_round(rng.dirichlet(np.full(K, 0.5), size=N)) if family == "comp_splotch_stan_model" else None
+    return synth.build_shared(sizes, pairs, eigs, rng.integers(1, C + 1, size=N), [1, 2], (2, 2), [1, 2], [],
+                              np.clip(rng.lognormal(0, 0.5, N), 0.05, 8), C, zi=1, car=1, E=E)
+
+
+@pytest.mark.parametrize("order", ["default", "cm", "generic"])
+@pytest.mark.parametrize("family", ["comp_splotch_stan_model", "splotch_stan_model_csr"])
+def test_lp_grad_all_kernel_paths(family, order, monkeypatch):
+    """The tiled TMA pipeline (given order / breadth-first relabelled order) and the generic two-phase
+    kernel must all reproduce the oracle, on a multi-tile design with shuffled spot order."""
+    if order != "default":
+        monkeypatch.setenv("CSPLOTCH_FORCE_ORDER", order)
+    shared = _shuffled_grid_design(3, family)
+    genes = synth.simulate_counts(shared, 3, 5)
+    b = _batch(shared, genes, family)
+    rng = np.random.default_rng(1)
+    theta = rng.normal(0, 1.0, (3, b.model.dim))
+    lp, grad = b.log_prob_grad(theta, gene_of=np.arange(3))
+    o = oracle.Oracle(synth.gene_dict(shared, genes, 0), family)
+    lp0, g0 = o.log_prob_grad_batch(genes["counts"], theta, gene_of=np.arange(3),
+                                    prior_mean=genes.get("beta_prior_mean"), prior_std=genes.get("beta_prior_std"))
+    assert np.max(np.abs(lp - lp0) / np.abs(lp0)) < 1e-10
+    assert _rel(grad, g0) < 1e-10
+    # leapfrog + write_array through the same path
+    p0 = rng.normal(0, 1, (3, b.model.dim))
+    minv = rng.uniform(0.3, 2.0, (3, b.model.dim))
+    th, p, H = b.leapfrog_fixed(theta * 0.3, p0, minv, 1e-3, 16, gene_of=np.arange(3))
+    for i in range(3):
+        oi = oracle.Oracle(synth.gene_dict(shared, genes, i), family)
+        th0, pp0, H0 = oi.leapfrog_fixed(theta[i] * 0.3, p0[i], minv[i], 1e-3, 16)
+        assert _rel(th[i], th0) < 1e-8 and _rel(p[i], pp0) < 1e-8 and abs(H[i] - H0) < 1e-8 * abs(H0)
+        assert np.allclose(b.write_array(theta[i:i + 1], gene_of=[i])[0], oi.write_array(theta[i]), rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("order", ["default", "generic"])
+def test_nuts_multi_tile_matches_oracle(order, monkeypatch):
+    if order != "default":
+        monkeypatch.setenv("CSPLOTCH_FORCE_ORDER", order)
+    family = "comp_splotch_stan_model"
+    shared = _shuffled_grid_design(4, family, side=24)
+    genes = synth.simulate_counts(shared, 2, 6)
+    b = _batch(shared, genes, family, gene_id0=3)
+    cfg = api.nuts_cfg(20, 5, 2, seed=9)
+    s = api.Sampler(b, cfg)
+    ocfg = oracle.nuts_cfg(20, 5, seed=9)
+    want = {}
+    for g in range(2):
+        o = oracle.Oracle(synth.gene_dict(shared, genes, g), family)
+        for c in range(2):
+            want[g, c] = o.nuts(ocfg, gene_id=3 + g, chain_id=c + 1, save_warmup=True)
+    for it in range(6):
+        s.advance(1)
+        th, eps, mi = s.state()
+        for (g, c), w in want.items():
+            assert np.max(np.abs(th[g, c] - w["draws"][it, 7:])) < 1e-7, (it, g, c)
+            assert abs(eps[g, c] - w["draws"][it + 1, 2]) < 1e-7 * eps[g, c]
+
+
 @pytest.mark.parametrize("family", FAMS)
 def test_write_array_matches_oracle(family):
     shared, genes = _tiny(family, 3, 1, 1, seed=31)
