@@ -292,9 +292,9 @@ class Sampler:
         return dict(n_leapfrog=a.value, n_grad=b.value, n_divergent=c.value, n_launches=d.value)
 
     def profile(self):
-        out = (C.c_int64 * 6)()
+        out = (C.c_int64 * 8)()
         check(self.lib.csplotch_sampler_profile(self.h, out))
-        keys = ["cyc_eval", "cyc_merge", "cyc_copy", "cyc_other", "n_merge", "n_copy"]
+        keys = ["cyc_eval", "cyc_merge", "cyc_copy", "cyc_other", "n_merge", "n_copy", "cyc_pro", "cyc_fin"]
         return dict(zip(keys, [int(x) for x in out]))
 
     def status(self):

@@ -196,7 +196,7 @@ __global__ void k_summ_finalize(const double *__restrict__ summ, const ChainScal
 // ------------------------------------------------------------------------------------------------
 // main kernels
 // ------------------------------------------------------------------------------------------------
-// dynamic shared memory: B[nbeta] | adjB[nbeta] | red | mbar[4] | ring[4T] | phr[2T] | mst[2T] | psi slots | rest slots
+// dynamic shared memory: B[nbeta] | adjB[nbeta] | red | mbar[5] | tdesc | ring[4T] | psi slots | rest slots
 template <int KT>
 __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, double *smem) {
   ops.B = smem;
@@ -204,20 +204,18 @@ __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, do
   ops.red = smem + 2 * m.nbeta;
   double *p = ops.red + kWarps * kRedMax;
   ops.mbar = reinterpret_cast<uint64_t *>(p);
-  p += 4;
+  p += 6;
+  ops.tdesc = reinterpret_cast<TmaDesc *>(p);
+  p += (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 2;
   ops.ring = p;
   p += 4 * kTile;
-  ops.phr = p;
-  p += 2 * kTile;
-  ops.mst = p;
-  p += 2 * kTile;
   ops.psi_st = p;
-  p += 8 * kTile;
+  p += 12 * kTile;
   ops.rest_st = reinterpret_cast<unsigned char *>(p);
   ops.tile_seq = 0;
   if (m.tiled) {
     if (threadIdx.x == 0) {
-      for (int i = 0; i < 4; ++i) mbar_init(ops.mbar + i, 1);
+      for (int i = 0; i < 5; ++i) mbar_init(ops.mbar + i, 1);
       mbar_fence_init();
     }
     __syncthreads();
@@ -329,18 +327,18 @@ k_nuts_advance(const __grid_constant__ DevModel m, const __grid_constant__ Sampl
     ops.sample_is_q0 = true;
     const size_t ns = (size_t)s.cfg.num_samples;
     ops.out_diag = s.diag ? s.diag + (size_t)w * ns * 7 : nullptr;
-    ops.out_small = s.small ? s.small + (size_t)w * ns * m.nsmall : nullptr;
+    ops.out_small = s.small ? s.small + (size_t)w * ns * m.nsmall_true : nullptr;
     ops.out_theta = s.theta ? s.theta + (size_t)w * ns * m.D : nullptr;
     ops.out_summ = s.summ ? s.summ + (size_t)w * 6 * m.N : nullptr;
     ChainScalars cs = s.cs[w];
-    ops.cyc_eval = ops.cyc_merge = ops.cyc_copy = ops.cyc_other = ops.n_merge = ops.n_copy = 0;
+    ops.cyc_eval = ops.cyc_merge = ops.cyc_copy = ops.cyc_other = ops.n_merge = ops.n_copy = ops.cyc_pro = ops.cyc_fin = 0;
     const long long t_chain = clock64();
     Nuts<DevOps<KT>> nuts(ops, s.cfg, cs, ops.key);
     nuts.advance(n_iter, s.have_init != 0);
     __syncthreads();
     if (threadIdx.x == 0) {
       cs.cyc_eval += ops.cyc_eval; cs.cyc_merge += ops.cyc_merge; cs.cyc_copy += ops.cyc_copy;
-      cs.n_merge += ops.n_merge; cs.n_copy += ops.n_copy;
+      cs.n_merge += ops.n_merge; cs.n_copy += ops.n_copy; cs.cyc_pro += ops.cyc_pro; cs.cyc_fin += ops.cyc_fin;
       cs.cyc_other += (clock64() - t_chain) - ops.cyc_eval - ops.cyc_merge - ops.cyc_copy;
       s.cs[w] = cs;
     }
@@ -362,12 +360,12 @@ extern "C" int32_t csplotch_set_device(int32_t device) {
   return CSPLOTCH_OK;
 }
 
+// internal (padded) number of cell types = the template instantiation; padded entries are dead
+// elements (E = 0, q = p = g = 0) exactly like padding spots
 static int pick_kt(int K) {
-  if (K <= 1) return 1;
-  if (K <= 4) return 4;
-  if (K <= 8) return 8;
-  if (K <= 12) return 12;
-  if (K <= 16) return 16;
+  const int opts[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+  for (int o : opts)
+    if (K <= o) return o;
   return 0;
 }
 
@@ -404,10 +402,11 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   m->kt = kt;
   DevModel &dm = m->dm;
   memset(&dm, 0, sizeof(dm));
-  dm.family = d->family; dm.N = N; dm.NT = (N + kTile - 1) / kTile; dm.Npad = dm.NT * kTile; dm.C = C; dm.K = K;
+  dm.family = d->family; dm.N = N; dm.NT = (N + kTile - 1) / kTile; dm.Npad = dm.NT * kTile; dm.C = C; dm.K = kt; dm.Ktrue = K;
   dm.L1 = L1; dm.L2 = L2; dm.L3 = L3; dm.L = L;
   dm.bot0 = L3 ? L1 + L2 : (L2 ? L1 : 0);
-  dm.nbeta = L * C * K;
+  dm.nbeta = L * C * kt;
+  dm.nbeta_true = L * C * K;
   dm.zi = zi; dm.car = car;
   int ns = 0;
   dm.s_tau = car ? ns++ : -1;
@@ -418,14 +417,15 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   dm.s_theta = zi ? ns++ : -1;
   dm.nscal = ns;
   dm.nsmall = dm.nbeta + ns;
+  dm.nsmall_true = dm.nbeta_true + ns;
   dm.nsmall_pad = (dm.nsmall + 1) & ~1;
   dm.o_psi = 0;
   dm.o_noise = car ? dm.Npad : 0;
   dm.o_small = dm.o_noise + dm.Npad;
   dm.Di = dm.o_small + dm.nsmall_pad;
-  dm.D = (car ? N : 0) + dm.nbeta + ns + N;
+  dm.D = (car ? N : 0) + dm.nbeta_true + ns + N;
   dm.Nc = dm.Npad;
-  m->n_outputs = dm.D + N + dm.nbeta;
+  m->n_outputs = dm.D + N + dm.nbeta_true;
 
   // ---- adjacency in original spot ids ---------------------------------------------------------------
   std::vector<std::vector<int>> adj0(car ? N : 0);
@@ -522,15 +522,15 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   dm.tiled = tiled ? 1 : 0;
   dm.ell_w = (car && tiled) ? ell_w : 0;
   dm.stage_bytes = (5 * kTile) * (int)sizeof(double) + (2 + dm.ell_w) * kTile * (int)sizeof(int);
-  m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 4) * sizeof(double);
-  if (tiled) m->smem_bytes += (size_t)(4 + 2 + 2 + 8) * kTile * sizeof(double) + 2 * (size_t)dm.stage_bytes;
+  m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 6) * sizeof(double) + (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 16;
+  if (tiled) m->smem_bytes += (size_t)(4 + 12) * kTile * sizeof(double) + 2 * (size_t)dm.stage_bytes;
   if (m->smem_bytes > 220 * 1024) {
     delete m;
     return fail(CSPLOTCH_E_UNSUPPORTED, "beta table (L*C*K) too large for shared memory");
   }
 
   // Stan offsets (declaration order)
-  const int so_psi = 0, so_beta = car ? N : 0, so_scal = so_beta + dm.nbeta, so_noise = so_scal + ns;
+  const int so_psi = 0, so_beta = car ? N : 0, so_scal = so_beta + dm.nbeta_true, so_noise = so_scal + ns;
   m->imap.assign(dm.Di, -1);
   for (int j = 0; j < N; ++j) {
     if (car) m->imap[dm.o_psi + j] = so_psi + m->perm[j];
@@ -539,8 +539,8 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   for (int i = 0; i < L; ++i)
     for (int j = 0; j < C; ++j)
       for (int k = 0; k < K; ++k) {
-        const int internal = (i * C + j) * K + k;
-        const int stan = d->family == CSPLOTCH_COMP_SPLOTCH ? internal : i + L * j;
+        const int internal = (i * C + j) * kt + k;
+        const int stan = d->family == CSPLOTCH_COMP_SPLOTCH ? (i * C + j) * K + k : i + L * j;
         m->imap[dm.o_small + internal] = so_beta + stan;
       }
   for (int s = 0; s < ns; ++s) m->imap[dm.o_small + dm.nbeta + s] = so_scal + s;
@@ -561,7 +561,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
       if (d->D[jo] < 1 || d->D[jo] > C) { delete m; return fail(CSPLOTCH_E_INVALID, "D out of range"); }
       if (!(d->size_factors[jo] > 0)) { delete m; return fail(CSPLOTCH_E_INVALID, "size_factors must be > 0"); }
       lsf[ji] = std::log(d->size_factors[jo]);
-      key[ji] = tissue_of[jo] * C + (d->D[jo] - 1);
+      key[ji] = (tissue_of[jo] * C + (d->D[jo] - 1)) | ((car ? (int)adj0[jo].size() : 0) << 24);
     }
   }
   std::vector<int> map2(L2), map3(L3);
@@ -595,10 +595,10 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   }
   std::vector<double> E;
   if (d->family == CSPLOTCH_COMP_SPLOTCH) {
-    E.assign((size_t)dm.NT * K * kTile, 0.0);
+    E.assign((size_t)dm.NT * kt * kTile, 0.0);
     for (int ji = 0; ji < N; ++ji)
       for (int k = 0; k < K; ++k)
-        E[((size_t)(ji / kTile) * K + k) * kTile + (ji % kTile)] = d->E[(size_t)m->perm[ji] * K + k];
+        E[((size_t)(ji / kTile) * kt + k) * kTile + (ji % kTile)] = d->E[(size_t)m->perm[ji] * K + k];
   }
   bool ok = true;
   double *p_lsf, *p_E, *p_eu, *p_em;
@@ -629,8 +629,8 @@ extern "C" void csplotch_model_destroy(csplotch_model *m) { delete m; }
 
 extern "C" int32_t csplotch_model_dims(const csplotch_model *m, csplotch_dims *o) {
   if (!m || !o) return fail(CSPLOTCH_E_INVALID, "null argument");
-  o->N = m->dm.N; o->dim = m->dm.D; o->n_beta = m->dm.nbeta; o->n_scalar = m->dm.nscal;
-  o->n_small = m->dm.nsmall; o->n_outputs = m->n_outputs;
+  o->N = m->dm.N; o->dim = m->dm.D; o->n_beta = m->dm.nbeta_true; o->n_scalar = m->dm.nscal;
+  o->n_small = m->dm.nsmall_true; o->n_outputs = m->n_outputs;
   return CSPLOTCH_OK;
 }
 
@@ -650,9 +650,13 @@ static int batch_finish(csplotch_model *m, csplotch_batch *b, const int *counts_
   CU_TRY(cudaGetLastError());
   if (dm.family == CSPLOTCH_COMP_SPLOTCH) {
     if (!pm || !ps) return fail(CSPLOTCH_E_INVALID, "comp model needs beta_prior_mean / beta_prior_std");
-    std::vector<double> hm(pm, pm + (size_t)b->G * dm.K), hs(ps, ps + (size_t)b->G * dm.K);
-    for (double v : hs)
-      if (!(v > 0)) return fail(CSPLOTCH_E_INVALID, "beta_prior_std must be > 0");
+    std::vector<double> hm((size_t)b->G * dm.K, 0.0), hs((size_t)b->G * dm.K, 1.0);
+    for (int g = 0; g < b->G; ++g)
+      for (int k = 0; k < dm.Ktrue; ++k) {
+        hm[(size_t)g * dm.K + k] = pm[(size_t)g * dm.Ktrue + k];
+        hs[(size_t)g * dm.K + k] = ps[(size_t)g * dm.Ktrue + k];
+        if (!(ps[(size_t)g * dm.Ktrue + k] > 0)) return fail(CSPLOTCH_E_INVALID, "beta_prior_std must be > 0");
+      }
     CU_TRY(b->buf.upload(&b->pm, hm));
     CU_TRY(b->buf.upload(&b->ps, hs));
   }
@@ -702,8 +706,13 @@ static int sm_count() {
 #define DISPATCH_KT(kt, ...)                 \
   switch (kt) {                               \
     case 1: { constexpr int KT = 1; __VA_ARGS__; } break;   \
+    case 2: { constexpr int KT = 2; __VA_ARGS__; } break;   \
+    case 3: { constexpr int KT = 3; __VA_ARGS__; } break;   \
     case 4: { constexpr int KT = 4; __VA_ARGS__; } break;   \
+    case 5: { constexpr int KT = 5; __VA_ARGS__; } break;   \
+    case 6: { constexpr int KT = 6; __VA_ARGS__; } break;   \
     case 8: { constexpr int KT = 8; __VA_ARGS__; } break;   \
+    case 10: { constexpr int KT = 10; __VA_ARGS__; } break; \
     case 12: { constexpr int KT = 12; __VA_ARGS__; } break; \
     case 16: { constexpr int KT = 16; __VA_ARGS__; } break; \
     default: return fail(CSPLOTCH_E_UNSUPPORTED, "unsupported N_celltypes"); \
@@ -862,7 +871,7 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   A(&sd.wm2, (size_t)W * Di);
   A(&sd.ws, (size_t)sd.n_slots * (kPoolVecs + 6) * Di);
   A(&sd.diag, (size_t)W * ns * 7);
-  A(&sd.small, (size_t)W * ns * dm.nsmall);
+  A(&sd.small, (size_t)W * ns * dm.nsmall_true);
   A(&sd.summ, (size_t)W * 6 * dm.N);
   if (cfg->keep_draws) A(&sd.theta, (size_t)W * ns * dm.D);
   A(&sd.queue, 1);
@@ -879,7 +888,7 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   CU_TRY(cudaMemsetAsync(sd.ws, 0, (size_t)sd.n_slots * (kPoolVecs + 6) * Di * sizeof(double), s->stream));
   CU_TRY(cudaMemsetAsync(sd.summ, 0, (size_t)W * 6 * dm.N * sizeof(double), s->stream));
   CU_TRY(cudaMemsetAsync(sd.diag, 0, (size_t)W * ns * 7 * sizeof(double), s->stream));
-  CU_TRY(cudaMemsetAsync(sd.small, 0, (size_t)W * ns * dm.nsmall * sizeof(double), s->stream));
+  CU_TRY(cudaMemsetAsync(sd.small, 0, (size_t)W * ns * dm.nsmall_true * sizeof(double), s->stream));
   CU_TRY(cudaStreamSynchronize(s->stream));
   *out = s;
   return CSPLOTCH_OK;
@@ -957,15 +966,15 @@ extern "C" int32_t csplotch_sampler_counters(csplotch_sampler *s, int64_t *n_lea
   return CSPLOTCH_OK;
 }
 
-extern "C" int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out6) {
-  if (!s || !out6) return fail(CSPLOTCH_E_INVALID, "null argument");
+extern "C" int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out8) {
+  if (!s || !out8) return fail(CSPLOTCH_E_INVALID, "null argument");
   std::vector<ChainScalars> h;
   int rc = fetch_cs(s, h);
   if (rc) return rc;
-  for (int i = 0; i < 6; ++i) out6[i] = 0;
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
   for (auto &x : h) {
-    out6[0] += x.cyc_eval; out6[1] += x.cyc_merge; out6[2] += x.cyc_copy; out6[3] += x.cyc_other;
-    out6[4] += x.n_merge; out6[5] += x.n_copy;
+    out8[0] += x.cyc_eval; out8[1] += x.cyc_merge; out8[2] += x.cyc_copy; out8[3] += x.cyc_other;
+    out8[4] += x.n_merge; out8[5] += x.n_copy; out8[6] += x.cyc_pro; out8[7] += x.cyc_fin;
   }
   return CSPLOTCH_OK;
 }
@@ -988,7 +997,7 @@ extern "C" int32_t csplotch_sampler_get_draws(csplotch_sampler *s, double *diag,
   const size_t ns = (size_t)s->cfg.num_samples, W = (size_t)s->sd.W;
   CU_TRY(cudaStreamSynchronize(s->stream));
   if (diag) CU_TRY(cudaMemcpy(diag, s->sd.diag, W * ns * 7 * sizeof(double), cudaMemcpyDeviceToHost));
-  if (small) CU_TRY(cudaMemcpy(small, s->sd.small, W * ns * dm.nsmall * sizeof(double), cudaMemcpyDeviceToHost));
+  if (small) CU_TRY(cudaMemcpy(small, s->sd.small, W * ns * dm.nsmall_true * sizeof(double), cudaMemcpyDeviceToHost));
   if (n_draws) {
     std::vector<ChainScalars> h;
     int rc = fetch_cs(s, h);
@@ -1079,7 +1088,7 @@ k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm,
     Scalars sc;
     ops.load_small(q, sc);
     // constrained parameters in declaration order (Stan index space)
-    const int so_beta = m.car ? m.N : 0, so_scal = so_beta + m.nbeta;
+    const int so_beta = m.car ? m.N : 0, so_scal = so_beta + m.nbeta_true;
     for (int e = threadIdx.x; e < m.Di; e += kBlock) {
       const int si = m.imap[e];
       if (si < 0) continue;
@@ -1098,7 +1107,7 @@ k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm,
       if (si >= so_beta && si < so_scal) {
         const int internal = e - m.o_small;
         const int i = internal / CK, rem = internal - i * CK, j = rem / m.K, k = rem - j * m.K;
-        oi = so_beta + i + m.L * (j + m.C * k);
+        oi = so_beta + i + m.L * (j + m.C * k);   // k < Ktrue here: padded entries have imap = -1
       }
       o[oi] = v;
     }
@@ -1106,7 +1115,7 @@ k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm,
     double *oll = o + m.D;
     const double sig03 = 0.3 * sc.sigma;
     for (int j = threadIdx.x; j < m.N; j += kBlock) {
-      const double *bj = ops.B + (m.bot0 * m.C) * m.K + m.key[j] * m.K;
+      const double *bj = ops.B + (m.bot0 * m.C) * m.K + (m.key[j] & 0xFFFFFF) * m.K;
       double ll = 0.0;
       if (KT == 1) ll = bj[0];
       else {
@@ -1120,10 +1129,12 @@ k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm,
     double *ob = oll + m.N;
     for (int idx = threadIdx.x; idx < m.nbeta; idx += kBlock) {
       const int i = idx / CK, rem = idx - i * CK, j = rem / m.K, k = rem - j * m.K;
+      if (k >= m.Ktrue) continue;
+      const int CKt = m.C * m.Ktrue;
       int lev0, nr, off;
       if (i < m.L1) { lev0 = 0; nr = m.L1; off = 0; }
-      else if (i < m.L1 + m.L2) { lev0 = m.L1; nr = m.L2; off = m.L1 * CK; }
-      else { lev0 = m.L1 + m.L2; nr = m.L3; off = (m.L1 + m.L2) * CK; }
+      else if (i < m.L1 + m.L2) { lev0 = m.L1; nr = m.L2; off = m.L1 * CKt; }
+      else { lev0 = m.L1 + m.L2; nr = m.L3; off = (m.L1 + m.L2) * CKt; }
       ob[off + (i - lev0) + nr * (j + m.C * k)] = ops.B[idx];
     }
     __syncthreads();

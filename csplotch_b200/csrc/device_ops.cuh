@@ -30,6 +30,7 @@ constexpr int kMaxEll = 8;       // widest ELL adjacency the tiled path takes (V
 
 struct DevModel {
   int family, N, Npad, C, K, L1, L2, L3, L, bot0, nbeta, nscal, nsmall, nsmall_pad;
+  int Ktrue, nbeta_true, nsmall_true;  // K is the padded (template) cell-type count; *_true are Stan's
   int zi, car;
   int D;   // Stan dimension
   int Di;  // internal dimension (padded)
@@ -42,7 +43,7 @@ struct DevModel {
   int ell_w;   // ELL width (max degree), 0 without CAR
   int stage_bytes;
   const double *lsf;     // [Npad] log(size_factors), 0 in the padding
-  const int *key;        // [Npad] bottom-level bin: (tissue_mapping[t]-1)*C + D_j-1, -1 in the padding
+  const int *key;        // [Npad] bits 0-23 bottom-level bin (tissue_mapping[t]-1)*C + D_j-1, bits 24-27 degree; -1 = padding
   const int *rowptr;     // [N+1] CSR of the symmetric adjacency (internal spot ids)
   const int *col;        // [2 W_n]
   const int *ell;        // [NT][ell_w][kTile] neighbour spot ids, -1 = none
@@ -175,6 +176,18 @@ __device__ __forceinline__ bool lane_owns_bin(int lane) {
   return (lane & ((1 << sh) - 1)) == 0;
 }
 
+// One TMA bulk copy per tile and input stream, described once per call in shared memory so that the
+// lanes of warp 0 can issue all of a tile's copies in parallel (a single issuing thread made warp 0
+// the straggler of every tile).
+struct TmaDesc {
+  const unsigned char *src;  // stream base (tile 0)
+  uint32_t tile_bytes;       // bytes per tile = advance per tile
+  uint32_t dst_off;          // byte offset inside the slot
+  uint32_t group;            // 0: psi block (two tiles ahead), 1: the rest (one tile ahead)
+  uint32_t pad_;
+};
+constexpr int kMaxDesc = 12;
+
 template <int KT>
 struct DevOps {
   const DevModel &m;
@@ -185,10 +198,11 @@ struct DevOps {
   double *B, *adjB, *red;
   uint64_t *mbar;        // "tile landed" barriers: [0,1] psi slots, [2,3] rest slots
   double *ring;          // drifted psi of tiles k-1, k, k+1 (+1 spare): ring[j & (4 T - 1)]
-  double *phr, *mst;     // half-kicked psi momenta / inverse metric of tiles k, k+1: [(tile & 1) * T + t]
-  double *psi_st;        // 2 slots x {q,p,g,minv}[T] of the psi block (TMA destination)
+  double *psi_st;        // 3 slots x {q,p,g,minv}[T] of the psi block (TMA destination); tile x in slot x mod 3
   unsigned char *rest_st;  // 2 slots x stage_bytes: {q,p,g,minv}[T] of noise_raw, lsf[T], counts[T], key[T], ell[w][T]
-  uint32_t tile_seq;     // tiles consumed so far by this CTA, mod 4 (slot = seq & 1, parity = (seq >> 1) & 1)
+  uint32_t tile_seq;     // tiles consumed so far by this CTA, mod 12: psi slot seq % 3 (parity (seq / 3) & 1),
+                         // rest slot seq & 1 (parity (seq >> 1) & 1)
+  TmaDesc *tdesc;        // kMaxDesc TMA stream descriptors (shared memory)
   // HBM vectors of this CTA slot / chain
   double *pool;         // kPoolVecs x Di
   double *zq[2], *zg[2];
@@ -200,7 +214,7 @@ struct DevOps {
   double *out_small;  // [num_samples][nsmall]
   double *out_theta;  // [num_samples][D] Stan order
   double *out_summ;   // [6][N]: mean,M2 of log_lambda | mean,M2 of lambda | mean,M2 of psi
-  long long cyc_eval = 0, cyc_merge = 0, cyc_copy = 0, cyc_other = 0, n_merge = 0, n_copy = 0;
+  long long cyc_eval = 0, cyc_merge = 0, cyc_copy = 0, cyc_other = 0, n_merge = 0, n_copy = 0, cyc_pro = 0, cyc_fin = 0;
 
   __device__ __forceinline__ DevOps(const DevModel &mm) : m(mm) {}
 
@@ -279,7 +293,8 @@ struct DevOps {
   template <bool LEAP>
   __device__ void finish(const Scalars &sc, double a_lp, double a_ng, double a_qD, double a_qW, double a_dth,
                          double a_kin, double a_g2, double tails, double *dq, double *dg, double *dp, double eps,
-                         double *V_out, double *K_out, bool *finite_out) {
+                         double *V_out, double *K_out, bool *finite_out, const double *sp = nullptr,
+                         double *rho_out = nullptr, double a_pp = 0.0, double *pp_out = nullptr) {
     const int tid = threadIdx.x;
     // log-determinant term of the CAR prior over the distinct eigenvalues
     double a_ldet = 0, a_dldet = 0;
@@ -335,10 +350,15 @@ struct DevOps {
         const double pn = dp[m.o_small + idx] + 0.5 * eps * gr;
         dp[m.o_small + idx] = pn;
         a_kin2 += minv[m.o_small + idx] * pn * pn;
+        if (rho_out) {
+          const double po = sp[m.o_small + idx];
+          a_pp += minv[m.o_small + idx] * po * pn;
+          rho_out[m.o_small + idx] = po + pn;
+        }
       }
     }
-    double r2[4] = {a_ds2, a_ds3, a_kin2, a_g2b};
-    block_sum<4>(r2, red);
+    double r2[5] = {a_ds2, a_ds3, a_kin2, a_g2b, a_pp};
+    block_sum<5>(r2, red);
 
     // scalars: every thread computes them (uniform), thread 0 stores
     double lp = r1[0] + sc.jac;
@@ -366,7 +386,8 @@ struct DevOps {
       gu_theta = sc.theta * (1.0 - sc.theta) * d_theta + (jacobian ? (1.0 - 2.0 * sc.theta) : 0.0);
     }
     // read phase (all threads) then write phase (thread 0) of the scalar momenta
-    double pn_s[6] = {0, 0, 0, 0, 0, 0};
+    double pn_s[6] = {0, 0, 0, 0, 0, 0}, po_s[6] = {0, 0, 0, 0, 0, 0};
+    double pp = r2[4];
     const double gu[6] = {gu_tau, gu_a, gu_sigma, gu_s2, gu_s3, gu_theta};
     const int sidx[6] = {m.s_tau, m.s_a, m.s_sigma, m.s_s2, m.s_s3, m.s_theta};
 #pragma unroll
@@ -376,6 +397,10 @@ struct DevOps {
         if (LEAP) {
           pn_s[s] = dp[so + sidx[s]] + 0.5 * eps * gu[s];
           kin += minv[so + sidx[s]] * pn_s[s] * pn_s[s];
+          if (rho_out) {
+            po_s[s] = sp[so + sidx[s]];
+            pp += minv[so + sidx[s]] * po_s[s] * pn_s[s];
+          }
         }
       }
     }
@@ -386,14 +411,17 @@ struct DevOps {
         if (sidx[s] >= 0) {
           dg[so + sidx[s]] = -gu[s];
           if (LEAP) dp[so + sidx[s]] = pn_s[s];
+          if (LEAP && rho_out) rho_out[so + sidx[s]] = po_s[s] + pn_s[s];
         }
       }
       for (int s = m.nsmall; s < m.nsmall_pad; ++s) {
         dg[m.o_small + s] = 0.0;
         if (LEAP) dp[m.o_small + s] = 0.0;
+        if (LEAP && rho_out) rho_out[m.o_small + s] = 0.0;
       }
     }
     __syncthreads();
+    if (pp_out) *pp_out = pp;
     if (V_out) *V_out = -lp;
     if (K_out) *K_out = 0.5 * kin;
     if (finite_out) *finite_out = isfinite(lp) && isfinite(g2);
@@ -412,105 +440,120 @@ struct DevOps {
   // local memory (the functions are __noinline__), so member / model-field accesses inside the loop would
   // be dependent generic loads on the critical path.
   struct TileCtx {
-    int NT, K, ell_w, car, zi, o_psi, o_noise, stage_bytes, bin0;
-    uint32_t seq0;
-    const double *E, *lsf_g, *minv_g;
-    const int *key_g, *ell_g, *cnt_g;
-    double *ring, *phr, *mst, *psi_st, *Bbot, *adjB;
+    int NT, ell_w, car, zi, o_psi, o_noise, stage_bytes, n_desc;
+    uint32_t seq0, psi_tx, rest_tx;
+    const double *E;
+    double *ring, *psi_st, *Bbot, *bins;
     unsigned char *rest_st;
     uint64_t *mbar;
+    const TmaDesc *desc;
   };
-  __device__ __forceinline__ TileCtx make_ctx() const {
+  template <bool LEAP>
+  __device__ __forceinline__ TileCtx make_ctx(const double *sq, const double *sg, const double *sp) {
     TileCtx c;
-    c.NT = m.NT; c.K = m.K; c.ell_w = m.ell_w; c.car = m.car; c.zi = m.zi;
+    c.NT = m.NT; c.ell_w = m.ell_w; c.car = m.car; c.zi = m.zi;
     c.o_psi = m.o_psi; c.o_noise = m.o_noise; c.stage_bytes = m.stage_bytes;
-    c.bin0 = (m.bot0 * m.C) * m.K;
+    const int bin0 = (m.bot0 * m.C) * KT;
     c.seq0 = tile_seq;
-    c.E = m.E; c.lsf_g = m.lsf; c.minv_g = minv; c.key_g = m.key; c.ell_g = m.ell; c.cnt_g = gn.counts;
-    c.ring = ring; c.phr = phr; c.mst = mst; c.psi_st = psi_st; c.Bbot = B + c.bin0; c.adjB = adjB;
+    c.E = m.E;
+    c.ring = ring; c.psi_st = psi_st; c.Bbot = B + bin0; c.bins = adjB + bin0;
     c.rest_st = rest_st; c.mbar = mbar;
+    c.desc = tdesc;
+    constexpr uint32_t vb = kTile * sizeof(double), ib = kTile * sizeof(int);
+    const int n_psi = m.car ? (LEAP ? 4 : 1) : 0;
+    const int n_rest = (LEAP ? 4 : 1) + 3 + (m.car ? 1 : 0);
+    c.n_desc = n_psi + n_rest;
+    c.psi_tx = (uint32_t)n_psi * vb;
+    c.rest_tx = (LEAP ? 4 * vb : vb) + vb + 2 * ib + (m.car ? (uint32_t)m.ell_w * ib : 0u);
+    // descriptor table (thread i writes descriptor i)
+    const int t = threadIdx.x;
+    if (t < c.n_desc) {
+      TmaDesc d;
+      d.pad_ = 0;
+      if (t < n_psi) {
+        const double *base = t == 0 ? sq : (t == 1 ? sp : (t == 2 ? sg : minv));
+        d.src = reinterpret_cast<const unsigned char *>(base + m.o_psi);
+        d.tile_bytes = vb; d.dst_off = (uint32_t)t * vb; d.group = 0;
+      } else {
+        const int r = t - n_psi;
+        const int nv = LEAP ? 4 : 1;
+        d.group = 1;
+        if (r < nv) {
+          const double *base = r == 0 ? sq : (r == 1 ? sp : (r == 2 ? sg : minv));
+          d.src = reinterpret_cast<const unsigned char *>(base + m.o_noise);
+          d.tile_bytes = vb; d.dst_off = (uint32_t)r * vb;
+        } else if (r == nv) {
+          d.src = reinterpret_cast<const unsigned char *>(m.lsf); d.tile_bytes = vb; d.dst_off = 4 * vb;
+        } else if (r == nv + 1) {
+          d.src = reinterpret_cast<const unsigned char *>(gn.counts); d.tile_bytes = ib; d.dst_off = 5 * vb;
+        } else if (r == nv + 2) {
+          d.src = reinterpret_cast<const unsigned char *>(m.key); d.tile_bytes = ib; d.dst_off = 5 * vb + ib;
+        } else {
+          d.src = reinterpret_cast<const unsigned char *>(m.ell); d.tile_bytes = (uint32_t)m.ell_w * ib;
+          d.dst_off = 5 * vb + 2 * ib;
+        }
+      }
+      tdesc[t] = d;
+    }
     return c;
   }
-  // Both pipelines are two slots deep: tile k lives in slot (seq0 + k) & 1 and (seq0 + k) >> 1 counts its
-  // uses.  psi inputs run two tiles ahead (the drift of tile k+1 precedes the gradient of tile k), the rest one.
-  template <bool LEAP>
-  static __device__ __forceinline__ void issue_psi(const TileCtx &c, int k, const double *sq, const double *sg,
-                                                   const double *sp) {
-    const uint32_t seq = c.seq0 + (uint32_t)k;
-    uint64_t *bar = c.mbar + (seq & 1u);
-    double *d = c.psi_st + (size_t)(seq & 1u) * 4 * kTile;
-    const size_t off = (size_t)c.o_psi + (size_t)k * kTile;
-    constexpr uint32_t vb = kTile * sizeof(double);
-    mbar_expect_tx(bar, LEAP ? 4 * vb : vb);
-    bulk_g2s(d, sq + off, vb, bar);
-    if (LEAP) {
-      bulk_g2s(d + kTile, sp + off, vb, bar);
-      bulk_g2s(d + 2 * kTile, sg + off, vb, bar);
-      bulk_g2s(d + 3 * kTile, c.minv_g + off, vb, bar);
+  // psi inputs run two tiles ahead (the drift of tile k+1 precedes the gradient of tile k, which still
+  // reads p, g, minv of its own tile) in three slots; the rest one tile ahead in two slots.  Called by
+  // every lane of warp 0 at trip k: issues psi(k+2) and rest(k+1).
+  static __device__ __forceinline__ void issue_tiles(const TileCtx &c, int k) {
+    const int lane = threadIdx.x;  // warp 0: lane == tid
+    if (lane == 0 && c.car && k + 2 >= 0 && k + 2 < c.NT)
+      mbar_expect_tx(c.mbar + ((c.seq0 + (uint32_t)(k + 2)) % 3u), c.psi_tx);
+    if (lane == 1 && k + 1 >= 0 && k + 1 < c.NT)
+      mbar_expect_tx(c.mbar + 3 + ((c.seq0 + (uint32_t)(k + 1)) & 1u), c.rest_tx);
+    __syncwarp();
+    if (lane < c.n_desc) {
+      const TmaDesc d = c.desc[lane];
+      const int tile = k + (d.group == 0 ? 2 : 1);
+      if (tile >= 0 && tile < c.NT) {
+        const uint32_t seq = c.seq0 + (uint32_t)tile;
+        const uint32_t slot = d.group == 0 ? seq % 3u : (seq & 1u);
+        unsigned char *dst = d.group == 0 ? reinterpret_cast<unsigned char *>(c.psi_st) + slot * (4 * kTile * sizeof(double))
+                                          : c.rest_st + (size_t)slot * c.stage_bytes;
+        bulk_g2s(dst + d.dst_off, d.src + (size_t)tile * d.tile_bytes, d.tile_bytes, c.mbar + 3 * d.group + slot);
+      }
     }
   }
-  template <bool LEAP>
-  static __device__ __forceinline__ void issue_rest(const TileCtx &c, int k, const double *sq, const double *sg,
-                                                    const double *sp) {
-    const uint32_t seq = c.seq0 + (uint32_t)k;
-    uint64_t *bar = c.mbar + 2 + (seq & 1u);
-    double *d = reinterpret_cast<double *>(c.rest_st + (size_t)(seq & 1u) * c.stage_bytes);
-    int *ip = reinterpret_cast<int *>(d + 5 * kTile);
-    const size_t toff = (size_t)k * kTile, off = (size_t)c.o_noise + toff;
-    constexpr uint32_t vb = kTile * sizeof(double), ib = kTile * sizeof(int);
-    mbar_expect_tx(bar, (LEAP ? 4 * vb : vb) + vb + 2 * ib + (c.car ? (uint32_t)c.ell_w * ib : 0u));
-    bulk_g2s(d, sq + off, vb, bar);
-    if (LEAP) {
-      bulk_g2s(d + kTile, sp + off, vb, bar);
-      bulk_g2s(d + 2 * kTile, sg + off, vb, bar);
-      bulk_g2s(d + 3 * kTile, c.minv_g + off, vb, bar);
-    }
-    bulk_g2s(d + 4 * kTile, c.lsf_g + toff, vb, bar);
-    bulk_g2s(ip, c.cnt_g + toff, ib, bar);
-    bulk_g2s(ip + kTile, c.key_g + toff, ib, bar);
-    if (c.car) bulk_g2s(ip + 2 * kTile, c.ell_g + (size_t)k * c.ell_w * kTile, (uint32_t)c.ell_w * ib, bar);
-  }
-  // drift psi of tile k into the ring; keep the half-kicked momentum and the metric for the gradient phase
+  // drift psi of tile k into the ring
   template <bool LEAP>
   static __device__ __forceinline__ void drift_tile(const TileCtx &c, int k, double eps) {
     const int t = threadIdx.x;
     const uint32_t seq = c.seq0 + (uint32_t)k;
-    mbar_wait(c.mbar + (seq & 1u), (seq >> 1) & 1u);
-    const double *d = c.psi_st + (size_t)(seq & 1u) * 4 * kTile;
+    mbar_wait(c.mbar + (seq % 3u), (seq / 3u) & 1u);
+    const double *d = c.psi_st + (size_t)(seq % 3u) * 4 * kTile;
     double qn = d[t];
-    if (LEAP) {
-      const double mi = d[3 * kTile + t];
-      const double ph = d[kTile + t] - 0.5 * eps * d[2 * kTile + t];
-      qn += eps * mi * ph;
-      c.phr[(k & 1) * kTile + t] = ph;
-      c.mst[(k & 1) * kTile + t] = mi;
-    }
+    if (LEAP) qn += eps * d[3 * kTile + t] * (d[kTile + t] - 0.5 * eps * d[2 * kTile + t]);
     c.ring[((k & 3) * kTile) + t] = qn;
   }
 
-  // per-tile contribution of one warp to the bottom-level bins: G[key][k] += sum_lanes gj * E[lane][k]
+  // per-tile contribution of one warp to the bottom-level bins: G[bin][k] += sum_lanes gj * E[lane][k]
   template <int KP>
-  static __device__ __forceinline__ void add_bins(double *bins, int K, double (&v)[KP], int key_l) {
+  static __device__ __forceinline__ void add_bins(double *bins, double (&v)[KP], int bin_l) {
     const int lane = threadIdx.x & 31;
-    const int k0 = __shfl_sync(0xffffffffu, key_l, 0);
-    if (__all_sync(0xffffffffu, key_l == k0)) {
-      if (k0 < 0) return;
+    const int b0 = __shfl_sync(0xffffffffu, bin_l, 0);
+    if (__all_sync(0xffffffffu, bin_l == b0)) {
+      if (b0 < 0) return;
       warp_transpose_sum<KP>(v);
       const int b = bin_of_lane<KP>(lane);
-      if (lane_owns_bin<KP>(lane) && b < K) atomicAdd(&bins[k0 * K + b], v[0]);
+      if (lane_owns_bin<KP>(lane) && b < KT) atomicAdd(&bins[b0 * KT + b], v[0]);
       return;
     }
-    unsigned remaining = __ballot_sync(0xffffffffu, key_l >= 0);
+    unsigned remaining = __ballot_sync(0xffffffffu, bin_l >= 0);
     while (remaining) {
       const int leader = __ffs(remaining) - 1;
-      const int kk = __shfl_sync(0xffffffffu, key_l, leader);
-      const bool mine = key_l == kk;
+      const int kk = __shfl_sync(0xffffffffu, bin_l, leader);
+      const bool mine = bin_l == kk;
       double w[KP];
 #pragma unroll
       for (int i = 0; i < KP; ++i) w[i] = mine ? v[i] : 0.0;
       warp_transpose_sum<KP>(w);
       const int b = bin_of_lane<KP>(lane);
-      if (lane_owns_bin<KP>(lane) && b < K) atomicAdd(&bins[kk * K + b], w[0]);
+      if (lane_owns_bin<KP>(lane) && b < KT) atomicAdd(&bins[kk * KT + b], w[0]);
       remaining &= ~__ballot_sync(0xffffffffu, mine);
     }
   }
@@ -518,23 +561,22 @@ struct DevOps {
   template <bool LEAP>
   __device__ __noinline__ void eval_tiled(const double *__restrict__ sq, const double *__restrict__ sg,
                                           const double *__restrict__ sp, double *dq, double *dg, double *dp,
-                                          double eps, double *V_out, double *K_out, bool *finite_out) {
-    constexpr int KP = KT <= 1 ? 1 : (KT <= 4 ? 4 : (KT <= 8 ? 8 : 16));
+                                          double eps, double *V_out, double *K_out, bool *finite_out,
+                                          double *rho_out, double *pp_out) {
+    constexpr int KP = KT <= 1 ? 1 : (KT <= 2 ? 2 : (KT <= 4 ? 4 : (KT <= 8 ? 8 : 16)));
     const int tid = threadIdx.x;
-    const TileCtx c = make_ctx();
+    const long long t_begin = clock64();
+    const TileCtx c = make_ctx<LEAP>(sq, sg, sp);
     const int NT = c.NT;
     const bool write_q = LEAP || dq != sq;
     // generic-proxy writes of earlier passes (q, p, g of this chain) must be visible to the async proxy
-    // (TMA) that is about to read them
+    // (TMA) that is about to read them; the barrier also publishes the descriptor table
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
     // the first tiles start streaming while the small block is prepared
-    if (tid == 0) {
-      if (c.car) {
-        issue_psi<LEAP>(c, 0, sq, sg, sp);
-        if (NT > 1) issue_psi<LEAP>(c, 1, sq, sg, sp);
-      }
-      issue_rest<LEAP>(c, 0, sq, sg, sp);
+    if (tid < 32) {
+      issue_tiles(c, -2);
+      issue_tiles(c, -1);
     }
     // small block: half-kick + drift (or copy), then constrained scalars and beta levels
     for (int e = m.o_small + tid; e < m.Di; e += kBlock) {
@@ -550,74 +592,65 @@ struct DevOps {
     Scalars sc;
     load_small(dq, sc);
     for (int idx = tid; idx < m.nbeta; idx += kBlock) adjB[idx] = 0.0;
-    const double heads = c.zi ? log(sc.theta) : 0.0;
     const double tails = c.zi ? log1p(-sc.theta) : 0.0;
     const double sig03 = 0.3 * sc.sigma;
-    const double theta = sc.theta, tau = sc.tau, a_car = sc.a;
-    const double inv_theta = c.zi ? 1.0 / theta : 0.0, inv_1mtheta = c.zi ? 1.0 / (1.0 - theta) : 0.0;
-    double *const dq_psi = dq + c.o_psi, *const dq_eps = dq + c.o_noise;
-    double *const dg_psi = dg + c.o_psi, *const dg_eps = dg + c.o_noise;
-    double *const dp_psi = dp + c.o_psi, *const dp_eps = dp + c.o_noise;
-    double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0;
+    const double theta = sc.theta, om_theta = 1.0 - sc.theta, tau = sc.tau, a_car = sc.a;
+    const double half_eps = 0.5 * eps;
+    double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0, a_pp = 0;
+    const bool merge0 = LEAP && rho_out != nullptr;
 
     if (c.car) drift_tile<LEAP>(c, 0, eps);
+    const long long t_loop = clock64();
     for (int k = 0; k < NT; ++k) {
       // cell-type fractions of this tile straight from L2 (gene-shared, coalesced per k); issued before
       // the barrier so that their latency overlaps the drift of the next tile and the barrier wait
-      double e[KT];
+      double e[KP];
       if (KT > 1) {
-        const double *Ej = c.E + ((size_t)k * c.K) * kTile + tid;
+        const double *Ej = c.E + ((size_t)k * KT) * kTile + tid;
 #pragma unroll
-        for (int i = 0; i < KT; ++i) e[i] = (i < c.K) ? __ldg(Ej + (size_t)i * kTile) : 0.0;
+        for (int i = 0; i < KP; ++i) e[i] = (i < KT) ? __ldg(Ej + (size_t)i * kTile) : 0.0;
       } else {
         e[0] = 1.0;
       }
       if (c.car && k + 1 < NT) drift_tile<LEAP>(c, k + 1, eps);
       __syncthreads();  // ring(k+1) complete; every thread is done with the gradient of tile k-1
-      if (tid == 0) {
-        if (c.car && k + 2 < NT) issue_psi<LEAP>(c, k + 2, sq, sg, sp);  // slot of tile k: drifted one trip ago
-        if (k + 1 < NT) issue_rest<LEAP>(c, k + 1, sq, sg, sp);          // slot of tile k-1
-      }
+      if (tid < 32) issue_tiles(c, k);  // psi(k+2) and rest(k+1) into the slots tile k-1 has just released
       const uint32_t seq = c.seq0 + (uint32_t)k;
-      mbar_wait(c.mbar + 2 + (seq & 1u), (seq >> 1) & 1u);
+      mbar_wait(c.mbar + 3 + (seq & 1u), (seq >> 1) & 1u);
+      const double *pd = c.psi_st + (size_t)(seq % 3u) * 4 * kTile;  // q, p, g, minv of psi, tile k
       const double *rd = reinterpret_cast<const double *>(c.rest_st + (size_t)(seq & 1u) * c.stage_bytes);
       const int *ri = reinterpret_cast<const int *>(rd + 5 * kTile);
       const int j = k * kTile + tid;
-      const int kj = ri[kTile + tid];  // -1 in the padding
+      const int kraw = ri[kTile + tid];  // -1 in the padding
+      const int bin = kraw < 0 ? -1 : (kraw & 0xFFFFFF);
       double gj = 0.0;
-      double ge[KP];
-#pragma unroll
-      for (int i = 0; i < KP; ++i) ge[i] = 0.0;
-      if (kj >= 0) {
+      if (kraw >= 0) {
         // noise_raw: drift in registers
         double eps_j = rd[tid], ph_e = 0.0, m_e = 0.0;
         if (LEAP) {
           m_e = rd[3 * kTile + tid];
-          ph_e = rd[kTile + tid] - 0.5 * eps * rd[2 * kTile + tid];
+          ph_e = rd[kTile + tid] - half_eps * rd[2 * kTile + tid];
           eps_j += eps * m_e * ph_e;
         }
-        const double *bj = c.Bbot + kj * c.K;
+        const double *bj = c.Bbot + bin * KT;
         double ll;
         if (KT == 1) {
           ll = bj[0];
         } else {
           ll = 0.0;
 #pragma unroll
-          for (int i = 0; i < KT; ++i)
-            if (i < c.K) ll += bj[i] * e[i];
+          for (int i = 0; i < KT; ++i) ll += bj[i] * e[i];
         }
         double psi_j = 0.0, Wpsi = 0.0, deg = 0.0;
         if (c.car) {
           psi_j = c.ring[j & (4 * kTile - 1)];
+          deg = (double)(kraw >> 24);
           const int *el = ri + 2 * kTile + tid;
 #pragma unroll
           for (int w = 0; w < kMaxEll; ++w) {
             if (w < c.ell_w) {
               const int nb = el[w * kTile];
-              if (nb >= 0) {
-                Wpsi += c.ring[nb & (4 * kTile - 1)];
-                deg += 1.0;
-              }
+              if (nb >= 0) Wpsi += c.ring[nb & (4 * kTile - 1)];
             }
           }
           ll += psi_j;
@@ -627,16 +660,15 @@ struct DevOps {
         const double mu = exp(eta);
         const int y = ri[tid];
         if (c.zi && y == 0) {
-          const double Bq = tails - mu;
-          const double dd = heads - Bq;
-          const double tt = exp(-fabs(dd));
-          const double l1p = log1p(tt);
-          const double wmax = 1.0 / (1.0 + tt), wmin = tt * wmax;
-          const double wA = dd >= 0 ? wmax : wmin;
-          const double wB = dd >= 0 ? wmin : wmax;
-          a_lp += (dd >= 0 ? heads : Bq) + l1p;
-          gj = -wB * mu;
-          a_dth += wA * inv_theta - wB * inv_1mtheta;
+          // log(theta + (1-theta) e^{-mu}) = log_sum_exp(log theta, log1m theta - mu); the two softmax
+          // weights are theta / s and z / s
+          const double em = exp(-mu);
+          const double z = om_theta * em;
+          const double s = theta + z;
+          const double inv_s = 1.0 / s;
+          a_lp += log(s);
+          gj = -(mu * z) * inv_s;
+          a_dth += (1.0 - em) * inv_s;
         } else {
           a_lp += (double)y * eta - mu;
           gj = (double)y - mu;
@@ -645,60 +677,81 @@ struct DevOps {
         a_ng += eps_j * gj;
         const double gr_eps = sig03 * gj - eps_j;
         a_g2 += gr_eps * gr_eps;
-        dg_eps[j] = -gr_eps;
-        if (write_q) dq_eps[j] = eps_j;
+        dg[c.o_noise + j] = -gr_eps;
+        if (write_q) dq[c.o_noise + j] = eps_j;
         if (LEAP) {
-          const double pn = ph_e + 0.5 * eps * gr_eps;
-          dp_eps[j] = pn;
+          const double pn = ph_e + half_eps * gr_eps;
+          dp[c.o_noise + j] = pn;
           a_kin += m_e * pn * pn;
+          if (merge0) {
+            const double po = rd[kTile + tid];
+            a_pp += m_e * po * pn;
+            rho_out[c.o_noise + j] = po + pn;
+          }
         }
         if (c.car) {
           a_qD += (psi_j * deg) * psi_j;
           a_qW += Wpsi * psi_j;
           const double gr_psi = gj - tau * (deg * psi_j - a_car * Wpsi);
           a_g2 += gr_psi * gr_psi;
-          dg_psi[j] = -gr_psi;
-          if (write_q) dq_psi[j] = psi_j;
+          dg[c.o_psi + j] = -gr_psi;
+          if (write_q) dq[c.o_psi + j] = psi_j;
           if (LEAP) {
-            const double pn = c.phr[(k & 1) * kTile + tid] + 0.5 * eps * gr_psi;
-            dp_psi[j] = pn;
-            a_kin += c.mst[(k & 1) * kTile + tid] * pn * pn;
+            const double po = pd[kTile + tid], mi = pd[3 * kTile + tid];
+            const double pn = (po - half_eps * pd[2 * kTile + tid]) + half_eps * gr_psi;
+            dp[c.o_psi + j] = pn;
+            a_kin += mi * pn * pn;
+            if (merge0) {
+              a_pp += mi * po * pn;
+              rho_out[c.o_psi + j] = po + pn;
+            }
           }
         }
-#pragma unroll
-        for (int i = 0; i < KT; ++i) ge[i] = gj * e[i];
       } else {
         // padding spots carry q = p = g = 0
-        dg_eps[j] = 0.0;
-        if (write_q) dq_eps[j] = 0.0;
-        if (LEAP) dp_eps[j] = 0.0;
+        dg[c.o_noise + j] = 0.0;
+        if (write_q) dq[c.o_noise + j] = 0.0;
+        if (LEAP) dp[c.o_noise + j] = 0.0;
+        if (merge0) rho_out[c.o_noise + j] = 0.0;
         if (c.car) {
-          dg_psi[j] = 0.0;
-          if (write_q) dq_psi[j] = 0.0;
-          if (LEAP) dp_psi[j] = 0.0;
+          dg[c.o_psi + j] = 0.0;
+          if (write_q) dq[c.o_psi + j] = 0.0;
+          if (LEAP) dp[c.o_psi + j] = 0.0;
+          if (merge0) rho_out[c.o_psi + j] = 0.0;
         }
       }
-      add_bins<KP>(c.adjB + c.bin0, c.K, ge, kj);
+#pragma unroll
+      for (int i = 0; i < KP; ++i) e[i] *= gj;
+      add_bins<KP>(c.bins, e, bin);
     }
-    tile_seq = (c.seq0 + (uint32_t)NT) & 3u;
-    finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out);
+    tile_seq = (c.seq0 + (uint32_t)NT) % 12u;
+    const long long t_fin = clock64();
+    // the zi-only part of d/dtheta was accumulated as (1 - e^{-mu}) / s; finish() expects it in a_dth
+    finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out, sp, rho_out,
+                 a_pp, pp_out);
+    cyc_pro += t_loop - t_begin;
+    cyc_fin += clock64() - t_fin;
   }
 
   // ---- fused [half-kick, drift,] log-density + gradient [, half-kick] ------------------------
   // LEAP: (sq,sg,sp) --eps--> (dq,dg,dp).  !LEAP: dq := sq (if different), dg := -grad lp(sq).
   // g vectors hold the gradient of the potential V = -lp, like Stan's ps_point::g.
   template <bool LEAP>
+  // rho_out != nullptr (LEAP only): also the level-0 U-turn merge of the previous leaf with this one, i.e.
+  // rho_out = sp + p_new and *pp_out = sum minv * sp * p_new (nuts_core.h), fused into the same pass
   __device__ void eval(const double *sq, const double *sg, const double *sp, double *dq, double *dg,
-                       double *dp, double eps, double *V_out, double *K_out, bool *finite_out) {
-    if (m.tiled) eval_tiled<LEAP>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out);
-    else eval_generic<LEAP>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out);
+                       double *dp, double eps, double *V_out, double *K_out, bool *finite_out,
+                       double *rho_out = nullptr, double *pp_out = nullptr) {
+    if (m.tiled) eval_tiled<LEAP>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
+    else eval_generic<LEAP>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
   }
 
   // Fallback for layouts the tiled pipeline does not take (neighbours further than one tile away or
   // degree > kMaxEll): two phases through HBM/L2 with a CSR gather.
   template <bool LEAP>
   __device__ __noinline__ void eval_generic(const double *sq, const double *sg, const double *sp, double *dq, double *dg,
-                               double *dp, double eps, double *V_out, double *K_out, bool *finite_out) {
+                               double *dp, double eps, double *V_out, double *K_out, bool *finite_out,
+                               double *rho_out, double *pp_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Di = m.Di;
     // phase A: half-kick + drift for every element (the spot loop below gathers psi of
@@ -733,7 +786,7 @@ struct DevOps {
     const double sig03 = 0.3 * sc.sigma;
     const double *psi = dq + m.o_psi;
     const double *noi = dq + m.o_noise;
-    double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0;
+    double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0, a_pp = 0;
     double acc[KT];
 #pragma unroll
     for (int k = 0; k < KT; ++k) acc[k] = 0.0;
@@ -749,7 +802,7 @@ struct DevOps {
       double gj = 0.0;
       double e[KT];
       if (act) {
-        kj = m.key[j];
+        kj = m.key[j] & 0xFFFFFF;
         const double eps_j = noi[j];
         double ll;
         const double *bj = B + (m.bot0 * m.C) * m.K + kj * m.K;
@@ -802,6 +855,11 @@ struct DevOps {
           const double pn = dp[m.o_noise + j] + 0.5 * eps * gr_eps;
           dp[m.o_noise + j] = pn;
           a_kin += minv[m.o_noise + j] * pn * pn;
+          if (rho_out) {
+            const double po = sp[m.o_noise + j];
+            a_pp += minv[m.o_noise + j] * po * pn;
+            rho_out[m.o_noise + j] = po + pn;
+          }
         }
         if (m.car) {
           a_qD += (psi_j * deg) * psi_j;
@@ -813,6 +871,11 @@ struct DevOps {
             const double pn = dp[m.o_psi + j] + 0.5 * eps * gr_psi;
             dp[m.o_psi + j] = pn;
             a_kin += minv[m.o_psi + j] * pn * pn;
+            if (rho_out) {
+              const double po = sp[m.o_psi + j];
+              a_pp += minv[m.o_psi + j] * po * pn;
+              rho_out[m.o_psi + j] = po + pn;
+            }
           }
         }
       }
@@ -831,10 +894,16 @@ struct DevOps {
     for (int j = m.N + tid; j < m.Npad; j += kBlock) {
       dg[m.o_noise + j] = 0.0;
       if (LEAP) dp[m.o_noise + j] = 0.0;
-      if (m.car) { dg[m.o_psi + j] = 0.0; if (LEAP) dp[m.o_psi + j] = 0.0; }
+      if (LEAP && rho_out) rho_out[m.o_noise + j] = 0.0;
+      if (m.car) {
+        dg[m.o_psi + j] = 0.0;
+        if (LEAP) dp[m.o_psi + j] = 0.0;
+        if (LEAP && rho_out) rho_out[m.o_psi + j] = 0.0;
+      }
     }
 
-    finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out);
+    finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out, sp, rho_out,
+                 a_pp, pp_out);
   }
 
   // ---- Ops interface of nuts_core.h ---------------------------------------------------------------
@@ -865,9 +934,10 @@ struct DevOps {
     cyc_eval += clock64() - t0;
     return V;
   }
-  __device__ void leapfrog(int zs, int ps, int zd, int pd, double eps, double *V, double *K) {
+  // rho0 >= 0: also rho0 := p(ps) + p(pd) and *pp = <p(ps), p(pd)>_M (level-0 U-turn merge fused in)
+  __device__ void leapfrog(int zs, int ps, int zd, int pd, double eps, double *V, double *K, int rho0, double *pp) {
     const long long t0 = clock64();
-    eval<true>(zq[zs], zg[zs], vec(ps), zq[zd], zg[zd], vec(pd), eps, V, K, nullptr);
+    eval<true>(zq[zs], zg[zs], vec(ps), zq[zd], zg[zd], vec(pd), eps, V, K, nullptr, rho0 >= 0 ? vec(rho0) : nullptr, pp);
     cyc_eval += clock64() - t0;
   }
   // Stan's three generalised U-turn criteria for the subtree L ++ C (base_nuts.hpp
@@ -972,7 +1042,16 @@ struct DevOps {
       r[4] = info.n_leapfrog; r[5] = info.divergent; r[6] = info.energy;
     }
     if (out_small)
-      for (int i = tid; i < m.nsmall; i += kBlock) out_small[(size_t)s * m.nsmall + i] = q_cur[m.o_small + i];
+      for (int i = tid; i < m.nsmall; i += kBlock) {
+        int o;
+        if (i < m.nbeta) {
+          const int row = i / m.K, k = i - row * m.K;
+          o = k < m.Ktrue ? row * m.Ktrue + k : -1;
+        } else {
+          o = m.nbeta_true + (i - m.nbeta);
+        }
+        if (o >= 0) out_small[(size_t)s * m.nsmall_true + o] = q_cur[m.o_small + i];
+      }
     if (out_theta)
       for (int e = tid; e < m.Di; e += kBlock) {
         const int si = m.imap[e];
@@ -987,7 +1066,7 @@ struct DevOps {
              *vla = out_summ + 3 * (size_t)m.N, *mps = out_summ + 4 * (size_t)m.N,
              *vps = out_summ + 5 * (size_t)m.N;
       for (int j = tid; j < m.N; j += kBlock) {
-        const double *bj = B + (m.bot0 * m.C) * m.K + m.key[j] * m.K;
+        const double *bj = B + (m.bot0 * m.C) * m.K + (m.key[j] & 0xFFFFFF) * m.K;
         double ll;
         if (KT == 1) {
           ll = bj[0];

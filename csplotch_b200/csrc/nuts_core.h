@@ -53,7 +53,7 @@ struct ChainScalars {
   long long n_leapfrog_total;  // sum of n_leapfrog__ over transitions
   long long n_grad_total;      // every gradient evaluation actually performed
   // device-side profile (SM clock cycles of this chain's CTA spent inside each collective op)
-  long long cyc_eval, cyc_merge, cyc_copy, cyc_other, n_merge, n_copy;
+  long long cyc_eval, cyc_merge, cyc_copy, cyc_other, n_merge, n_copy, cyc_pro, cyc_fin;
 };
 
 struct DrawInfo {
@@ -76,7 +76,8 @@ struct SubTree {
 // Ops (CTA-collective; every result is uniform over the CTA):
 //   double sample_momentum(int pvec, uint32_t purpose, uint32_t sub, uint32_t iter)   -> K = p'Minv p / 2
 //   double eval_at_current(int z, bool *finite)       z.q = q_cur, z.g = -grad lp(q_cur); returns V = -lp
-//   void   leapfrog(int zs, int ps, int zd, int pd, double eps, double *V, double *K)
+//   void   leapfrog(int zs, int ps, int zd, int pd, double eps, double *V, double *K, int rho0, double *pp)
+//          rho0 >= 0: also vec(rho0) = p(ps) + p(pd) and *pp = <p(ps), p(pd)>_M (fused level-0 merge)
 //   bool   merge(SubTree L, SubTree C, int rho_out)    three U-turn criteria of L ++ C; rho_out = rho(L)+rho(C)
 //   void   copy_q_to_prop(int z); void swap_prop_sample(); void commit_sample()
 //   void   init_uniform(uint32_t attempt, double radius); void set_unit_metric()
@@ -135,14 +136,19 @@ struct Nuts {
       SubTree cur{p0, p0, p0};
       int z_from = zsrc, p_from = psrc;
       const int nleaf = 1 << depth;
+      double K_prev = 0.0;
       for (int i = 0; i < nleaf; ++i) {
         Refs refs{0ull};
         refs.add(p_fwd); refs.add(p_bck); refs.add(rho_traj); refs.add(p_from);
         for (int k = 0; k < depth; ++k)
           if ((lvalid >> k) & 1u) { refs.add(L[k].pb); refs.add(L[k].pe); refs.add(L[k].rho); }
         const int pnew = pool_alloc(refs);
-        double Vn, Kn;
-        ops.leapfrog(z_from, p_from, Y, pnew, sign * cs.eps, &Vn, &Kn);
+        // an odd leaf closes a two-leaf subtree with its predecessor: that level-0 merge (rho = p_prev + p_new
+        // and <p_prev, p_new>_M) rides along in the leapfrog pass, where both momenta are in registers
+        const bool merge0 = (i & 1) != 0;
+        const int rho0 = merge0 ? pool_alloc(refs) : -1;
+        double Vn, Kn, pp_on = 0.0;
+        ops.leapfrog(z_from, p_from, Y, pnew, sign * cs.eps, &Vn, &Kn, rho0, &pp_on);
         ++n_leapfrog;
         double h = Vn + Kn;
         if (isnan(h)) h = INFINITY;
@@ -159,17 +165,25 @@ struct Nuts {
         if (divergent) { valid = false; break; }
         cur = SubTree{pnew, pnew, pnew};
         int k = 0;
+        if (merge0) {
+          // L = {p_prev}, C = {p_new}: all three criteria reduce to <p_prev, rho> > 0 and <p_new, rho> > 0
+          // with rho = p_prev + p_new, <p,p>_M = 2 K
+          const bool persist = (2.0 * Kn + pp_on > 0) && (2.0 * K_prev + pp_on > 0);
+          cur = SubTree{L[0].pb, pnew, rho0};
+          lvalid &= ~1u;
+          k = 1;
+          if (!persist) { valid = false; break; }
+        }
         while ((i >> k) & 1) {
-          const int rho_out = pool_alloc(refs);
-          const bool persist = ops.merge(L[k], cur, rho_out);
-          cur = SubTree{L[k].pb, cur.pe, rho_out};
-          lvalid &= ~(1u << k);
-          // the merged subtree keeps pb(L), pe(C), rho_out; everything else becomes free
           refs.mask = 0ull;
           refs.add(p_fwd); refs.add(p_bck); refs.add(rho_traj);
           refs.add(cur.pb); refs.add(cur.pe); refs.add(cur.rho);
           for (int kk = 0; kk < depth; ++kk)
             if ((lvalid >> kk) & 1u) { refs.add(L[kk].pb); refs.add(L[kk].pe); refs.add(L[kk].rho); }
+          const int rho_out = pool_alloc(refs);
+          const bool persist = ops.merge(L[k], cur, rho_out);
+          cur = SubTree{L[k].pb, cur.pe, rho_out};
+          lvalid &= ~(1u << k);
           ++k;
           if (!persist) { valid = false; break; }
         }
@@ -177,6 +191,7 @@ struct Nuts {
         if (k < depth) { L[k] = cur; lvalid |= 1u << k; }
         z_from = Y;
         p_from = pnew;
+        K_prev = Kn;
       }
       if (!valid) break;
       ++depth;
@@ -229,7 +244,8 @@ struct Nuts {
     for (uint32_t attempt = 0;; ++attempt) {
       const double K0 = ops.sample_momentum(0, PURP_SS_MOMENTUM, attempt, tag_iter);
       double Vn, Kn;
-      ops.leapfrog(0, 0, 1, 1, cs.eps, &Vn, &Kn);
+      double pp_unused;
+      ops.leapfrog(0, 0, 1, 1, cs.eps, &Vn, &Kn, -1, &pp_unused);
       cs.n_grad_total += 1;
       double h = Vn + Kn;
       if (isnan(h)) h = INFINITY;

@@ -165,8 +165,9 @@ int32_t csplotch_sampler_last_ms(csplotch_sampler *s, float *ms);
 int32_t csplotch_sampler_counters(csplotch_sampler *s, int64_t *n_leapfrog, int64_t *n_grad,
                                   int64_t *n_divergent, int64_t *n_launches);
 /* device-side profile summed over chains: SM cycles inside {log-density/leapfrog, U-turn merge passes,
- * candidate copies, everything else}, then the number of merge passes and candidate copies */
-int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out6);
+ * candidate copies, everything else}, the number of merge passes and candidate copies, then the cycles of
+ * the log-density pass spent before its tile loop (prologue) and after it (reductions, small block) */
+int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out8);
 /* per-chain status [G][num_chains]: 0 ok, 1 initialisation failed, 2 step size search failed */
 int32_t csplotch_sampler_status(csplotch_sampler *s, int32_t *status, int32_t *iters_done);
 

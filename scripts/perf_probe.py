@@ -21,7 +21,7 @@ def probe(name, family, shared, G, nch, iters, chunk):
     pr = s.profile(); tot = sum(pr[k] for k in ("cyc_eval", "cyc_merge", "cyc_copy", "cyc_other"))
     cnt = s.counters()
     print(json.dumps(dict(shape=name, profile={k: round(pr[k] / tot, 3) for k in ("cyc_eval", "cyc_merge", "cyc_copy", "cyc_other")},
-                          cyc_per_eval=round(pr["cyc_eval"] / cnt["n_grad"]), cyc_per_merge=round(pr["cyc_merge"] / max(1, pr["n_merge"])),
+                          cyc_per_eval=round(pr["cyc_eval"] / cnt["n_grad"]), pro=round(pr["cyc_pro"] / cnt["n_grad"]), fin=round(pr["cyc_fin"] / cnt["n_grad"]), cyc_per_merge=round(pr["cyc_merge"] / max(1, pr["n_merge"])),
                           merges_per_leap=round(pr["n_merge"] / cnt["n_leapfrog"], 2), copies_per_leap=round(pr["n_copy"] / cnt["n_leapfrog"], 2))), flush=True)
     N, D = model.N, model.dim
     bl = 56 * D + 4 * N

@@ -42,7 +42,7 @@ struct HostOps {
     *finite = ok;
     return -lp;
   }
-  void leapfrog(int zs, int ps, int zd, int pd, double eps, double *V, double *K) {
+  void leapfrog(int zs, int ps, int zd, int pd, double eps, double *V, double *K, int rho0, double *pp) {
     const double *sq = zq[zs].data(), *sg = zg[zs].data(), *sp = vec(ps);
     double *dq = zq[zd].data(), *dg = zg[zd].data(), *dp = vec(pd);
     for (int i = 0; i < D; ++i) {
@@ -51,14 +51,20 @@ struct HostOps {
       dq[i] = sq[i] + eps * minv[i] * ph;
     }
     const double lp = fn(ctx, dq, tmp.data());
-    double k = 0;
+    double k = 0, pq = 0;
+    double *rho = rho0 >= 0 ? vec(rho0) : nullptr;
     for (int i = 0; i < D; ++i) {
       dg[i] = -tmp[i];
       dp[i] -= 0.5 * eps * dg[i];
       k += minv[i] * dp[i] * dp[i];
+      if (rho) {
+        pq += minv[i] * sp[i] * dp[i];
+        rho[i] = sp[i] + dp[i];
+      }
     }
     *V = -lp;
     *K = 0.5 * k;
+    *pp = pq;
   }
   bool merge(csp::SubTree L, csp::SubTree C, int rho_out) {
     const double *Lpb = vec(L.pb), *Lpe = vec(L.pe), *Lrho = vec(L.rho);
