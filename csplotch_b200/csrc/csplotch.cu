@@ -208,7 +208,7 @@ __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, do
   ops.tdesc = reinterpret_cast<TmaDesc *>(p);
   p += (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 2;
   ops.ring = p;
-  p += 4 * kTile;
+  p += 4 * kTile + 2;  // + the always-zero cell missing neighbours point at
   ops.psi_st = p;
   p += 12 * kTile;
   ops.rest_st = reinterpret_cast<unsigned char *>(p);
@@ -217,6 +217,8 @@ __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, do
     if (threadIdx.x == 0) {
       for (int i = 0; i < 5; ++i) mbar_init(ops.mbar + i, 1);
       mbar_fence_init();
+      ops.ring[4 * kTile] = 0.0;
+      ops.ring[4 * kTile + 1] = 0.0;
     }
     __syncthreads();
   }
@@ -228,9 +230,8 @@ k_lpgrad(const __grid_constant__ DevModel m, const int *__restrict__ counts, con
          const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz, int G,
          const double *__restrict__ theta_int, const int *__restrict__ gene_of, int Bn, double *lp_out,
          double *grad_int, int jacobian) {
-  extern __shared__ __align__(16) double smem[];
   DevOps<KT> ops(m);
-  bind_smem(ops, m, smem);
+  bind_smem(ops, m, smem_d);
   ops.jacobian = jacobian;
   ops.minv = nullptr;
   for (int b = blockIdx.x; b < Bn; b += gridDim.x) {
@@ -261,9 +262,8 @@ k_leapfrog_fixed(const __grid_constant__ DevModel m, const int *__restrict__ cou
                  const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz,
                  int G, double *q, double *p, double *g, const double *__restrict__ minv,
                  const int *__restrict__ gene_of, int Bn, double eps, int n_steps, double *H_out) {
-  extern __shared__ __align__(16) double smem[];
   DevOps<KT> ops(m);
-  bind_smem(ops, m, smem);
+  bind_smem(ops, m, smem_d);
   ops.jacobian = 1;
   for (int b = blockIdx.x; b < Bn; b += gridDim.x) {
     const int gi = gene_of ? gene_of[b] : (b % G);
@@ -293,12 +293,11 @@ k_leapfrog_fixed(const __grid_constant__ DevModel m, const int *__restrict__ cou
 template <int KT>
 __global__ void __launch_bounds__(kBlock, 2)
 k_nuts_advance(const __grid_constant__ DevModel m, const __grid_constant__ SamplerDev s, int n_iter) {
-  extern __shared__ __align__(16) double smem[];
   __shared__ int s_work;
   const size_t Di = m.Di;
   double *ws = s.ws + (size_t)blockIdx.x * (size_t)(kPoolVecs + 6) * Di;
   DevOps<KT> ops(m);
-  bind_smem(ops, m, smem);
+  bind_smem(ops, m, smem_d);
   ops.jacobian = 1;
   for (;;) {
     if (threadIdx.x == 0) s_work = atomicAdd(s.queue, 1);
@@ -458,6 +457,21 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     }
   }
 
+  // bottom-level bin of every spot (original order): (tissue_mapping[t]-1)*C + D_j-1
+  std::vector<int> bin0_of(N), tissue_idx(N);
+  {
+    int j = 0;
+    for (int t = 0; t < T; ++t) {
+      const int tm = d->tissue_mapping[t];
+      if (tm < 1 || tm > Lbot) { delete m; return fail(CSPLOTCH_E_INVALID, "tissue_mapping out of range"); }
+      for (int sidx = 0; sidx < d->N_spots[t]; ++sidx, ++j) {
+        if (d->D[j] < 1 || d->D[j] > C) { delete m; return fail(CSPLOTCH_E_INVALID, "D out of range"); }
+        bin0_of[j] = (tm - 1) * C + (d->D[j] - 1);
+        tissue_idx[j] = t;
+      }
+    }
+  }
+
   // ---- internal spot order ---------------------------------------------------------------------------
   // The model is invariant under any relabelling of spots.  The tiled kernel needs every neighbour in the
   // same or an adjacent tile of kTile spots.  Try the given order first (row-major arrays already satisfy
@@ -513,6 +527,19 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     }
     if (fits(cm)) { m->perm = cm; tiled = true; }
   }
+  // refinement: inside each tissue list the spots bin by bin (stable), when that still tiles.  A warp
+  // then sees one bin per tile almost always, so its contribution to the beta gradient is one transposed
+  // warp reduction instead of one per distinct bin (small ST tissues in file order mix all AARs in a warp).
+  if (tiled && !(force && std::string(force) == "nosort")) {
+    std::vector<int> cand = m->perm;
+    std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+      if (tissue_idx[a] != tissue_idx[b]) return tissue_idx[a] < tissue_idx[b];
+      return bin0_of[a] < bin0_of[b];
+    });
+    // tissues must stay contiguous for this to make sense: perm lists whole tissues one after another in
+    // both the given and the breadth-first order (components never straddle tissues)
+    if (cand != m->perm && fits(cand)) m->perm = cand;
+  }
   if (force && std::string(force) == "generic") tiled = false;
   std::vector<int> inv(N);
   for (int j = 0; j < N; ++j) inv[m->perm[j]] = j;
@@ -521,9 +548,9 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     for (int i = 0; i < N; ++i) ell_w = std::max(ell_w, (int)adj0[i].size());
   dm.tiled = tiled ? 1 : 0;
   dm.ell_w = (car && tiled) ? ell_w : 0;
-  dm.stage_bytes = (5 * kTile) * (int)sizeof(double) + (2 + dm.ell_w) * kTile * (int)sizeof(int);
+  dm.stage_bytes = (5 * kTile) * (int)sizeof(double) + 2 * kTile * (int)sizeof(int) + ((dm.ell_w + 1) / 2 * 2) * kTile * (int)sizeof(unsigned short);
   m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 6) * sizeof(double) + (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 16;
-  if (tiled) m->smem_bytes += (size_t)(4 + 12) * kTile * sizeof(double) + 2 * (size_t)dm.stage_bytes;
+  if (tiled) m->smem_bytes += ((size_t)(4 + 12) * kTile + 2) * sizeof(double) + 2 * (size_t)dm.stage_bytes;
   if (m->smem_bytes > 220 * 1024) {
     delete m;
     return fail(CSPLOTCH_E_UNSUPPORTED, "beta table (L*C*K) too large for shared memory");
@@ -548,21 +575,11 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   // per-spot tables
   std::vector<double> lsf(dm.Npad, 0.0);
   std::vector<int> key(dm.Npad, -1);
-  {
-    std::vector<int> tissue_of(N);
-    int j = 0;
-    for (int t = 0; t < T; ++t) {
-      const int tm = d->tissue_mapping[t];
-      if (tm < 1 || tm > Lbot) { delete m; return fail(CSPLOTCH_E_INVALID, "tissue_mapping out of range"); }
-      for (int s = 0; s < d->N_spots[t]; ++s, ++j) tissue_of[j] = tm - 1;
-    }
-    for (int ji = 0; ji < N; ++ji) {
-      const int jo = m->perm[ji];
-      if (d->D[jo] < 1 || d->D[jo] > C) { delete m; return fail(CSPLOTCH_E_INVALID, "D out of range"); }
-      if (!(d->size_factors[jo] > 0)) { delete m; return fail(CSPLOTCH_E_INVALID, "size_factors must be > 0"); }
-      lsf[ji] = std::log(d->size_factors[jo]);
-      key[ji] = (tissue_of[jo] * C + (d->D[jo] - 1)) | ((car ? (int)adj0[jo].size() : 0) << 24);
-    }
+  for (int ji = 0; ji < N; ++ji) {
+    const int jo = m->perm[ji];
+    if (!(d->size_factors[jo] > 0)) { delete m; return fail(CSPLOTCH_E_INVALID, "size_factors must be > 0"); }
+    lsf[ji] = std::log(d->size_factors[jo]);
+    key[ji] = bin0_of[jo] | ((car ? (int)adj0[jo].size() : 0) << 24);
   }
   std::vector<int> map2(L2), map3(L3);
   for (int i = 0; i < L2; ++i) {
@@ -573,10 +590,11 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     map3[i] = d->level_3_mapping[i] - 1;
     if (map3[i] < 0 || map3[i] >= L2) { delete m; return fail(CSPLOTCH_E_INVALID, "level_3_mapping out of range"); }
   }
-  std::vector<int> rowptr(N + 1, 0), col, ell;
+  std::vector<int> rowptr(N + 1, 0), col;
+  std::vector<unsigned short> ell;
   std::vector<double> eigu, eigm;
   if (car) {
-    if (tiled) ell.assign((size_t)dm.NT * dm.ell_w * kTile, -1);
+    if (tiled) ell.assign((size_t)dm.NT * dm.ell_w * kTile, (unsigned short)(4 * kTile));
     for (int i = 0; i < N; ++i) {
       std::vector<int> a;
       for (int nb : adj0[m->perm[i]]) a.push_back(inv[nb]);
@@ -585,7 +603,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
       col.insert(col.end(), a.begin(), a.end());
       if (tiled)
         for (size_t w = 0; w < a.size(); ++w)
-          ell[((size_t)(i / kTile) * dm.ell_w + w) * kTile + (i % kTile)] = a[w];
+          ell[((size_t)(i / kTile) * dm.ell_w + w) * kTile + (i % kTile)] = (unsigned short)(a[w] & (4 * kTile - 1));
     }
     // distinct eigenvalues with multiplicity (exact duplicates only; c3 has 24 identical arrays)
     std::map<double, double> mult;
@@ -602,7 +620,8 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   }
   bool ok = true;
   double *p_lsf, *p_E, *p_eu, *p_em;
-  int *p_key, *p_rp, *p_col, *p_m2, *p_m3, *p_imap, *p_ell;
+  int *p_key, *p_rp, *p_col, *p_m2, *p_m3, *p_imap;
+  unsigned short *p_ell;
   ok &= m->buf.upload(&p_lsf, lsf) == cudaSuccess;
   ok &= m->buf.upload(&p_key, key) == cudaSuccess;
   ok &= m->buf.upload(&p_rp, rowptr) == cudaSuccess;
@@ -1074,9 +1093,8 @@ __global__ void __launch_bounds__(kBlock, 2)
 k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm, const double *__restrict__ ps, int G,
               const double *__restrict__ theta_int, const int *__restrict__ gene_of, const int *__restrict__ perm,
               int Bn, double *out, int n_out) {
-  extern __shared__ __align__(16) double smem[];
   DevOps<KT> ops(m);
-  bind_smem(ops, m, smem);
+  bind_smem(ops, m, smem_d);
   ops.jacobian = 0;
   const int CK = m.C * m.K;
   for (int b = blockIdx.x; b < Bn; b += gridDim.x) {

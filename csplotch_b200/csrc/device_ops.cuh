@@ -46,7 +46,7 @@ struct DevModel {
   const int *key;        // [Npad] bits 0-23 bottom-level bin (tissue_mapping[t]-1)*C + D_j-1, bits 24-27 degree; -1 = padding
   const int *rowptr;     // [N+1] CSR of the symmetric adjacency (internal spot ids)
   const int *col;        // [2 W_n]
-  const int *ell;        // [NT][ell_w][kTile] neighbour spot ids, -1 = none
+  const unsigned short *ell;  // [NT][ell_w][kTile] ring positions of the neighbours (id & (4T-1)); 4T = none
   const double *E;       // [NT][K][kTile]  (tile-major, cell type, spot-in-tile): coalesced per k
   const double *eigu;    // [n_eig] distinct eigenvalues
   const double *eigm;    // [n_eig] multiplicities
@@ -62,6 +62,10 @@ struct GeneDev {
   double lgam;         // sum_{y>0} lgamma(y+1)   (kept only under `target +=`, i.e. zi=1)
   double nnz;          // #{y>0}
 };
+
+// the one dynamic shared-memory array of every kernel in this library; indexing it directly (instead of
+// through generic pointers kept in structs) lets ptxas emit LDS/STS/ATOMS with 32-bit addresses
+extern __shared__ __align__(16) double smem_d[];
 
 struct Scalars {
   double tau, a, sigma, s2, s3, theta;
@@ -443,8 +447,7 @@ struct DevOps {
     int NT, ell_w, car, zi, o_psi, o_noise, stage_bytes, n_desc;
     uint32_t seq0, psi_tx, rest_tx;
     const double *E;
-    double *ring, *psi_st, *Bbot, *bins;
-    unsigned char *rest_st;
+    int ring_o, psi_o, rest_o, Bbot_o, bins_o;  // offsets (in doubles) into smem_d
     uint64_t *mbar;
     const TmaDesc *desc;
   };
@@ -456,15 +459,17 @@ struct DevOps {
     const int bin0 = (m.bot0 * m.C) * KT;
     c.seq0 = tile_seq;
     c.E = m.E;
-    c.ring = ring; c.psi_st = psi_st; c.Bbot = B + bin0; c.bins = adjB + bin0;
-    c.rest_st = rest_st; c.mbar = mbar;
+    c.ring_o = (int)(ring - smem_d); c.psi_o = (int)(psi_st - smem_d);
+    c.rest_o = (int)(reinterpret_cast<double *>(rest_st) - smem_d);
+    c.Bbot_o = (int)(B - smem_d) + bin0; c.bins_o = (int)(adjB - smem_d) + bin0;
+    c.mbar = mbar;
     c.desc = tdesc;
     constexpr uint32_t vb = kTile * sizeof(double), ib = kTile * sizeof(int);
     const int n_psi = m.car ? (LEAP ? 4 : 1) : 0;
     const int n_rest = (LEAP ? 4 : 1) + 3 + (m.car ? 1 : 0);
     c.n_desc = n_psi + n_rest;
     c.psi_tx = (uint32_t)n_psi * vb;
-    c.rest_tx = (LEAP ? 4 * vb : vb) + vb + 2 * ib + (m.car ? (uint32_t)m.ell_w * ib : 0u);
+    c.rest_tx = (LEAP ? 4 * vb : vb) + vb + 2 * ib + (m.car ? (uint32_t)m.ell_w * (ib / 2) : 0u);
     // descriptor table (thread i writes descriptor i)
     const int t = threadIdx.x;
     if (t < c.n_desc) {
@@ -489,7 +494,7 @@ struct DevOps {
         } else if (r == nv + 2) {
           d.src = reinterpret_cast<const unsigned char *>(m.key); d.tile_bytes = ib; d.dst_off = 5 * vb + ib;
         } else {
-          d.src = reinterpret_cast<const unsigned char *>(m.ell); d.tile_bytes = (uint32_t)m.ell_w * ib;
+          d.src = reinterpret_cast<const unsigned char *>(m.ell); d.tile_bytes = (uint32_t)m.ell_w * (ib / 2);
           d.dst_off = 5 * vb + 2 * ib;
         }
       }
@@ -513,8 +518,9 @@ struct DevOps {
       if (tile >= 0 && tile < c.NT) {
         const uint32_t seq = c.seq0 + (uint32_t)tile;
         const uint32_t slot = d.group == 0 ? seq % 3u : (seq & 1u);
-        unsigned char *dst = d.group == 0 ? reinterpret_cast<unsigned char *>(c.psi_st) + slot * (4 * kTile * sizeof(double))
-                                          : c.rest_st + (size_t)slot * c.stage_bytes;
+        unsigned char *dst = d.group == 0
+                                 ? reinterpret_cast<unsigned char *>(smem_d + c.psi_o) + slot * (4 * kTile * sizeof(double))
+                                 : reinterpret_cast<unsigned char *>(smem_d + c.rest_o) + (size_t)slot * c.stage_bytes;
         bulk_g2s(dst + d.dst_off, d.src + (size_t)tile * d.tile_bytes, d.tile_bytes, c.mbar + 3 * d.group + slot);
       }
     }
@@ -525,15 +531,16 @@ struct DevOps {
     const int t = threadIdx.x;
     const uint32_t seq = c.seq0 + (uint32_t)k;
     mbar_wait(c.mbar + (seq % 3u), (seq / 3u) & 1u);
-    const double *d = c.psi_st + (size_t)(seq % 3u) * 4 * kTile;
+    const double *d = smem_d + c.psi_o + (seq % 3u) * 4 * kTile;
     double qn = d[t];
     if (LEAP) qn += eps * d[3 * kTile + t] * (d[kTile + t] - 0.5 * eps * d[2 * kTile + t]);
-    c.ring[((k & 3) * kTile) + t] = qn;
+    smem_d[c.ring_o + ((k & 3) * kTile) + t] = qn;
   }
 
   // per-tile contribution of one warp to the bottom-level bins: G[bin][k] += sum_lanes gj * E[lane][k]
   template <int KP>
-  static __device__ __forceinline__ void add_bins(double *bins, double (&v)[KP], int bin_l) {
+  static __device__ __forceinline__ void add_bins(int bins_o, double (&v)[KP], int bin_l) {
+    double *bins = smem_d + bins_o;
     const int lane = threadIdx.x & 31;
     const int b0 = __shfl_sync(0xffffffffu, bin_l, 0);
     if (__all_sync(0xffffffffu, bin_l == b0)) {
@@ -617,9 +624,10 @@ struct DevOps {
       if (tid < 32) issue_tiles(c, k);  // psi(k+2) and rest(k+1) into the slots tile k-1 has just released
       const uint32_t seq = c.seq0 + (uint32_t)k;
       mbar_wait(c.mbar + 3 + (seq & 1u), (seq >> 1) & 1u);
-      const double *pd = c.psi_st + (size_t)(seq % 3u) * 4 * kTile;  // q, p, g, minv of psi, tile k
-      const double *rd = reinterpret_cast<const double *>(c.rest_st + (size_t)(seq & 1u) * c.stage_bytes);
+      const double *pd = smem_d + c.psi_o + (seq % 3u) * 4 * kTile;  // q, p, g, minv of psi, tile k
+      const double *rd = smem_d + c.rest_o + (seq & 1u) * (c.stage_bytes >> 3);
       const int *ri = reinterpret_cast<const int *>(rd + 5 * kTile);
+      const double *ringp = smem_d + c.ring_o;
       const int j = k * kTile + tid;
       const int kraw = ri[kTile + tid];  // -1 in the padding
       const int bin = kraw < 0 ? -1 : (kraw & 0xFFFFFF);
@@ -632,7 +640,7 @@ struct DevOps {
           ph_e = rd[kTile + tid] - half_eps * rd[2 * kTile + tid];
           eps_j += eps * m_e * ph_e;
         }
-        const double *bj = c.Bbot + bin * KT;
+        const double *bj = smem_d + c.Bbot_o + bin * KT;
         double ll;
         if (KT == 1) {
           ll = bj[0];
@@ -643,16 +651,14 @@ struct DevOps {
         }
         double psi_j = 0.0, Wpsi = 0.0, deg = 0.0;
         if (c.car) {
-          psi_j = c.ring[j & (4 * kTile - 1)];
+          psi_j = ringp[j & (4 * kTile - 1)];
           deg = (double)(kraw >> 24);
-          const int *el = ri + 2 * kTile + tid;
+          // ELL entries are ring positions (neighbour id & (4T-1)); missing neighbours point at the
+          // always-zero cell ring[4T], so the gather is branch-free
+          const unsigned short *el = reinterpret_cast<const unsigned short *>(ri + 2 * kTile) + tid;
 #pragma unroll
-          for (int w = 0; w < kMaxEll; ++w) {
-            if (w < c.ell_w) {
-              const int nb = el[w * kTile];
-              if (nb >= 0) Wpsi += c.ring[nb & (4 * kTile - 1)];
-            }
-          }
+          for (int w = 0; w < kMaxEll; ++w)
+            if (w < c.ell_w) Wpsi += ringp[el[w * kTile]];
           ll += psi_j;
         }
         ll += sig03 * eps_j;
@@ -722,7 +728,7 @@ struct DevOps {
       }
 #pragma unroll
       for (int i = 0; i < KP; ++i) e[i] *= gj;
-      add_bins<KP>(c.bins, e, bin);
+      add_bins<KP>(c.bins_o, e, bin);
     }
     tile_seq = (c.seq0 + (uint32_t)NT) % 12u;
     const long long t_fin = clock64();
