@@ -116,7 +116,7 @@ def make_inputs(workload: str, genes_per_gpu: int, rank: int):
     return cfg["family"], shared, genes
 
 
-def cpu_reference_run(family, shared, genes, iters, n_threads, seconds_target=15.0, n_chains=4):
+def cpu_reference_run(family, shared, genes, iters, n_threads, n_chains=4):
     """Bounded CPU sample: n_threads gene-chains (one thread each, like CmdStan's one process per
     chain) for `iters` warm-up transitions from initialisation; returns (grads, seconds, description)."""
     import oracle
@@ -125,12 +125,21 @@ def cpu_reference_run(family, shared, genes, iters, n_threads, seconds_target=15
     G = min(G, genes["counts"].shape[0])
     o = oracle.Oracle(synth.gene_dict(shared, genes, 0), family)
     cfg = oracle.nuts_cfg(iters, 0, seed=1)
+    pm = genes["beta_prior_mean"][:G] if "beta_prior_mean" in genes else None
+    ps = genes["beta_prior_std"][:G] if "beta_prior_std" in genes else None
     t0 = time.time()
-    res = o.nuts_batch(genes["counts"][:G], cfg, n_chains=n_chains, prior_mean=genes.get("beta_prior_mean", [None])[:G] if "beta_prior_mean" in genes else None,
-                       prior_std=genes["beta_prior_std"][:G] if "beta_prior_std" in genes else None,
+    res = o.nuts_batch(genes["counts"][:G], cfg, n_chains=n_chains, prior_mean=pm, prior_std=ps,
                        n_threads=n_threads, want_draws=False)
     dt = time.time() - t0
-    return res["n_grad"], dt, "%d genes x %d chains x first %d NUTS transitions (from initialisation)" % (G, n_chains, iters)
+    return res["n_grad"], dt, "%d genes x %d chains x first %d NUTS transitions (from initialisation), %d threads" % (
+        G, n_chains, iters, n_threads)
+
+
+def cpu_iters_for(family, shared, genes, n_threads, target_s):
+    """Pick the number of transitions so that one bounded CPU sample takes about target_s seconds."""
+    g, dt, _ = cpu_reference_run(family, shared, genes, 2, n_threads)
+    per_iter = max(dt / 2.0, 1e-4)
+    return int(min(400, max(2, target_s / per_iter)))
 
 
 def run_reference(args):
@@ -143,9 +152,9 @@ def run_reference(args):
     family, shared, genes = make_inputs(args.workload, max(8, (os.cpu_count() or 8) // 4), 0)
     nthr = os.cpu_count() or 1
     N = int(np.sum(shared["N_spots"]))
-    iters = args.cpu_iters or (4 if N < 10000 else 1)
+    iters = args.cpu_iters or cpu_iters_for(family, shared, genes, nthr, 120.0 / max(1, args.steps + args.warmup))
     for _ in range(args.warmup):
-        cpu_reference_run(family, shared, genes, 1, nthr)
+        cpu_reference_run(family, shared, genes, iters, nthr)
     tot_g, tot_t, sample = 0, 0.0, ""
     for _ in range(args.steps):
         g, dt, sample = cpu_reference_run(family, shared, genes, iters, nthr)
@@ -317,7 +326,8 @@ def main():
         }
         if world == 1 and not args.no_cpu:
             nthr = os.cpu_count() or 1
-            cg, cdt, sample = cpu_reference_run(family, shared, genes, args.cpu_iters or (4 if N < 10000 else 1), nthr)
+            cg, cdt, sample = cpu_reference_run(family, shared, genes,
+                                                args.cpu_iters or cpu_iters_for(family, shared, genes, nthr, 15.0), nthr)
             line["cpu_baseline"] = {"value": cg / cdt, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample,
                                     "seconds": cdt,
                                     "note": "CPU restatement (oracle/), not CmdStan: CmdStan cannot be built in this image"}

@@ -120,14 +120,16 @@ def main(argv=None):
     except OSError:
         print("Error: Cannot create the output directory!", file=sys.stderr)
         return 1
-    # contiguous runs keep gene_id0 + i == gene id (RNG stream keyed by the gene index)
-    runs, cur = [], [gene_ids[0]]
-    for g in gene_ids[1:]:
-        if g == cur[-1] + 1 and len(cur) < a.batch:
-            cur.append(g)
-        else:
-            runs.append(cur); cur = [g]
-    runs.append(cur)
+    # one process per GPU under torchrun: this rank's contiguous block of the gene list, no collective
+    from . import shard
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:
+        gene_ids = shard.my_genes(sorted(gene_ids), world, rank)
+        a.device = int(os.environ.get("LOCAL_RANK", str(rank)))
+        if not gene_ids:
+            return 0
+    # contiguous runs keep gene_id0 + i == gene id (the RNG stream is keyed by the gene index)
+    runs = shard.contiguous_runs(gene_ids, a.batch)
     rc = 0
     for run in runs:
         try:

@@ -173,8 +173,9 @@ int32_t csplotch_sampler_status(csplotch_sampler *s, int32_t *status, int32_t *i
 
 /* sampling draws so far.
  * diag  [G][num_chains][num_samples][7]  lp__,accept_stat__,stepsize__,treedepth__,n_leapfrog__,divergent__,energy__
- * small [G][num_chains][num_samples][n_small]  beta_level_1..3 (each [Lk][C][K] row-major) are NOT here:
- *        this is the unconstrained small block (beta_raw | scalars) in Stan order;
+ * small [G][num_chains][num_samples][n_small]  the UNCONSTRAINED non-spot block: beta_raw[(i*C + j)*K + k]
+ *        (level-major rows, the same for all three families) followed by tau, a, sigma, sigma_level_2,
+ *        sigma_level_3, theta as present; beta_level_1..3 follow from it (csplotch_b200/api.py);
  * n_draws [G][num_chains] = sampling iterations completed. Any pointer may be NULL. */
 int32_t csplotch_sampler_get_draws(csplotch_sampler *s, double *diag, double *small, int32_t *n_draws);
 /* full unconstrained draws [G][num_chains][num_samples][dim] (needs cfg.keep_draws) */

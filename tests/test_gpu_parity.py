@@ -267,8 +267,10 @@ def _split_rhat(x):
 @pytest.mark.slow
 def test_posterior_matches_oracle_within_mcse():
     """Tier 3: posterior means of beta_level_1 and the scalars agree with the CPU oracle's NUTS
-    within Monte-Carlo standard error; R-hat < 1.01 needs longer chains than a unit test affords,
-    so the bound here is 1.05 on 4 x 500 draws."""
+    within Monte-Carlo standard error.  R-hat < 1.01 (north star) needs longer chains than a unit test
+    affords: on 4 x 500 draws of this 42-spot design the heavy-tailed tau reaches 1.10 on BOTH samplers
+    (CPU oracle: see profiles/r01_posterior_check.txt), so the bound here is 1.2 and the oracle's own
+    R-hat is checked against the same bound."""
     from csplotch_b200 import diagnostics as dg
     family = "comp_splotch_stan_model"
     shared, genes = _tiny(family, 2, 1, 1, seed=3, G=1)
@@ -288,7 +290,7 @@ def test_posterior_matches_oracle_within_mcse():
         got = ex[name][0].reshape(nch, ns)
         mcse = np.sqrt(ref.var() / max(dg.ess_bulk(ref), 10) + got.var() / max(dg.ess_bulk(got), 10))
         assert abs(got.mean() - ref.mean()) < 5 * mcse, (name, got.mean(), ref.mean(), mcse)
-        assert dg.split_rhat(got) < 1.05
+        assert dg.split_rhat(got) < 1.2 and dg.split_rhat(ref) < 1.2
     L1, C, K = b.model.levels[0], b.model.C, b.model.K
     raw_ref = dr[:, :, 7 + N:7 + N + L1 * C * K].reshape(nch, ns, L1, C, K)
     b1_ref = raw_ref * genes["beta_prior_std"][0] + genes["beta_prior_mean"][0]
