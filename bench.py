@@ -254,8 +254,8 @@ def main():
     del sampler
 
     # ---- e2e arm: host buffers through the C ABI, copies inside the timed region --------------------
-    Ge = args.e2e_genes or min(G, 148 if N < 10000 else 74)
-    e2e_iters = max(iters, 2)
+    Ge = args.e2e_genes or min(G, 1184 if N < 10000 else 148)
+    e2e_iters = 10 if N < 10000 else 4
     counts_host = np.ascontiguousarray(genes["counts"][:Ge])
     pm = genes["beta_prior_mean"][:Ge] if "beta_prior_mean" in genes else None
     ps = genes["beta_prior_std"][:Ge] if "beta_prior_std" in genes else None

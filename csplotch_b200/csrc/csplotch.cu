@@ -196,7 +196,11 @@ __global__ void k_summ_finalize(const double *__restrict__ summ, const ChainScal
 // ------------------------------------------------------------------------------------------------
 // main kernels
 // ------------------------------------------------------------------------------------------------
-// dynamic shared memory: B[nbeta] | adjB[nbeta] | red | mbar[5] | tdesc | ring[4T] | psi slots | rest slots
+// resident CTAs per SM: the non-compositional models (KT <= 2) need few enough registers for three
+template <int KT>
+constexpr int kCtasPerSm = KT <= 2 ? 3 : 2;
+static int ctas_per_sm(int kt) { return kt <= 2 ? 3 : 2; }
+// dynamic shared memory: B[nbeta] | adjB[nbeta] | red | mbar[9] | tdesc | ring[4T] | psi slots | rest slots
 template <int KT>
 __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, double *smem) {
   ops.B = smem;
@@ -204,7 +208,7 @@ __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, do
   ops.red = smem + 2 * m.nbeta;
   double *p = ops.red + kWarps * kRedMax;
   ops.mbar = reinterpret_cast<uint64_t *>(p);
-  p += 6;
+  p += 10;
   ops.tdesc = reinterpret_cast<TmaDesc *>(p);
   p += (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 2;
   ops.ring = p;
@@ -216,6 +220,7 @@ __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, do
   if (m.tiled) {
     if (threadIdx.x == 0) {
       for (int i = 0; i < 5; ++i) mbar_init(ops.mbar + i, 1);
+      for (int i = 5; i < 9; ++i) mbar_init(ops.mbar + i, kBlock);
       mbar_fence_init();
       ops.ring[4 * kTile] = 0.0;
       ops.ring[4 * kTile + 1] = 0.0;
@@ -225,7 +230,7 @@ __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, do
 }
 
 template <int KT>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
 k_lpgrad(const __grid_constant__ DevModel m, const int *__restrict__ counts, const double *__restrict__ pm,
          const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz, int G,
          const double *__restrict__ theta_int, const int *__restrict__ gene_of, int Bn, double *lp_out,
@@ -257,7 +262,7 @@ __global__ void k_negate(double *v, size_t n) {
 }
 
 template <int KT>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
 k_leapfrog_fixed(const __grid_constant__ DevModel m, const int *__restrict__ counts, const double *__restrict__ pm,
                  const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz,
                  int G, double *q, double *p, double *g, const double *__restrict__ minv,
@@ -291,7 +296,7 @@ k_leapfrog_fixed(const __grid_constant__ DevModel m, const int *__restrict__ cou
 }
 
 template <int KT>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
 k_nuts_advance(const __grid_constant__ DevModel m, const __grid_constant__ SamplerDev s, int n_iter) {
   __shared__ int s_work;
   const size_t Di = m.Di;
@@ -549,7 +554,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   dm.tiled = tiled ? 1 : 0;
   dm.ell_w = (car && tiled) ? ell_w : 0;
   dm.stage_bytes = (5 * kTile) * (int)sizeof(double) + 2 * kTile * (int)sizeof(int) + ((dm.ell_w + 1) / 2 * 2) * kTile * (int)sizeof(unsigned short);
-  m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 6) * sizeof(double) + (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 16;
+  m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 10) * sizeof(double) + (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 16;
   if (tiled) m->smem_bytes += ((size_t)(4 + 12) * kTile + 2) * sizeof(double) + 2 * (size_t)dm.stage_bytes;
   if (m->smem_bytes > 220 * 1024) {
     delete m;
@@ -757,7 +762,7 @@ extern "C" int32_t csplotch_log_prob_grad_dev(csplotch_batch *b, const double *t
   }
   const int nb = sm_count() * 8;
   k_to_internal<<<nb, 256, 0, st>>>(theta_dev, th_int, dm.imap, Bn, dm.D, dm.Di, 0.0);
-  const int grid = std::min(Bn, sm_count() * 2);
+  const int grid = std::min(Bn, sm_count() * ctas_per_sm(m->kt));
   cudaError_t e = cudaSuccess;
   DISPATCH_KT(m->kt, {
     e = set_smem(k_lpgrad<KT>, m->smem_bytes);
@@ -829,7 +834,7 @@ extern "C" int32_t csplotch_leapfrog_fixed(csplotch_batch *b, const double *thet
   k_to_internal<<<nb, 256>>>(stan, p, dm.imap, Bn, dm.D, dm.Di, 0.0);
   CU_TRY(cudaMemcpy(stan, inv_metric, nS * sizeof(double), cudaMemcpyHostToDevice));
   k_to_internal<<<nb, 256>>>(stan, mi, dm.imap, Bn, dm.D, dm.Di, 1.0);
-  const int grid = std::min(Bn, sm_count() * 2);
+  const int grid = std::min(Bn, sm_count() * ctas_per_sm(m->kt));
   cudaError_t e = cudaSuccess;
   DISPATCH_KT(m->kt, {
     e = set_smem(k_leapfrog_fixed<KT>, m->smem_bytes);
@@ -878,7 +883,7 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   sd.cfg = NutsConfig{cfg->num_warmup, cfg->num_samples, cfg->max_depth, cfg->delta, cfg->gamma, cfg->kappa, cfg->t0,
                       cfg->init_buffer, cfg->term_buffer, cfg->window, cfg->init_radius, cfg->stepsize, cfg->seed};
   sd.counts = b->counts; sd.pm = b->pm; sd.ps = b->ps; sd.lgam = b->lgam; sd.nnz = b->nnz;
-  s->grid = std::min(W, sm_count() * 2);
+  s->grid = std::min(W, sm_count() * ctas_per_sm(m->kt));
   sd.n_slots = s->grid;
   const size_t Di = dm.Di, ns = (size_t)cfg->num_samples;
   cudaError_t e = cudaSuccess;
@@ -1089,7 +1094,7 @@ extern "C" int32_t csplotch_sampler_get_spot_summaries(csplotch_sampler *s, doub
 // write_array is host-side glue over small per-draw blocks; the heavy part (log_lambda) is
 // evaluated on the device through the same load_small + spot loop as the sampler.
 template <int KT>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
 k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm, const double *__restrict__ ps, int G,
               const double *__restrict__ theta_int, const int *__restrict__ gene_of, const int *__restrict__ perm,
               int Bn, double *out, int n_out) {
@@ -1181,7 +1186,7 @@ extern "C" int32_t csplotch_write_array(csplotch_batch *b, const double *theta, 
   DISPATCH_KT(m->kt, {
     e = set_smem(k_write_array<KT>, m->smem_bytes);
     if (e == cudaSuccess)
-      k_write_array<KT><<<std::min(Bn, sm_count() * 2), kBlock, m->smem_bytes>>>(dm, b->pm, b->ps, b->G, q, go, perm_dev,
+      k_write_array<KT><<<std::min(Bn, sm_count() * ctas_per_sm(m->kt)), kBlock, m->smem_bytes>>>(dm, b->pm, b->ps, b->G, q, go, perm_dev,
                                                                                 Bn, o, m->n_outputs);
   });
   if (e == cudaSuccess) e = cudaGetLastError();

@@ -128,6 +128,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -200,7 +203,8 @@ struct DevOps {
   int jacobian;
   // shared memory: B[nbeta] | adjB[nbeta] | red[kWarps*kRedMax] | mbar[kStages] | ring[4 T] | phr[2 T] | stages
   double *B, *adjB, *red;
-  uint64_t *mbar;        // "tile landed" barriers: [0,1] psi slots, [2,3] rest slots
+  uint64_t *mbar;        // [0..2] psi slot landed (TMA), [3,4] rest slot landed (TMA), [5,6] psi of a tile is in the
+                         // ring (256 arrivals), [7,8] every thread is done with a tile's staged inputs (256 arrivals)
   double *ring;          // drifted psi of tiles k-1, k, k+1 (+1 spare): ring[j & (4 T - 1)]
   double *psi_st;        // 3 slots x {q,p,g,minv}[T] of the psi block (TMA destination); tile x in slot x mod 3
   unsigned char *rest_st;  // 2 slots x stage_bytes: {q,p,g,minv}[T] of noise_raw, lsf[T], counts[T], key[T], ell[w][T]
@@ -535,6 +539,7 @@ struct DevOps {
     double qn = d[t];
     if (LEAP) qn += eps * d[3 * kTile + t] * (d[kTile + t] - 0.5 * eps * d[2 * kTile + t]);
     smem_d[c.ring_o + ((k & 3) * kTile) + t] = qn;
+    mbar_arrive(c.mbar + 5 + (seq & 1u));  // "psi of tile k is in the ring" (256 arrivals per use)
   }
 
   // per-tile contribution of one warp to the bottom-level bins: G[bin][k] += sum_lanes gj * E[lane][k]
@@ -606,7 +611,10 @@ struct DevOps {
     double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0, a_pp = 0;
     const bool merge0 = LEAP && rho_out != nullptr;
 
-    if (c.car) drift_tile<LEAP>(c, 0, eps);
+    if (c.car) {
+      drift_tile<LEAP>(c, 0, eps);
+      mbar_wait(c.mbar + 5 + (c.seq0 & 1u), (c.seq0 >> 1) & 1u);  // ring(0); later tiles are awaited one ahead
+    }
     const long long t_loop = clock64();
     for (int k = 0; k < NT; ++k) {
       // cell-type fractions of this tile straight from L2 (gene-shared, coalesced per k); issued before
@@ -620,9 +628,12 @@ struct DevOps {
         e[0] = 1.0;
       }
       if (c.car && k + 1 < NT) drift_tile<LEAP>(c, k + 1, eps);
-      __syncthreads();  // ring(k+1) complete; every thread is done with the gradient of tile k-1
-      if (tid < 32) issue_tiles(c, k);  // psi(k+2) and rest(k+1) into the slots tile k-1 has just released
       const uint32_t seq = c.seq0 + (uint32_t)k;
+      if (tid < 32) {
+        // psi(k+2) and rest(k+1) go into the slots of tile k-1: wait until every thread has released them
+        if (k > 0) mbar_wait(c.mbar + 7 + ((seq - 1u) & 1u), ((seq - 1u) >> 1) & 1u);
+        issue_tiles(c, k);
+      }
       mbar_wait(c.mbar + 3 + (seq & 1u), (seq >> 1) & 1u);
       const double *pd = smem_d + c.psi_o + (seq % 3u) * 4 * kTile;  // q, p, g, minv of psi, tile k
       const double *rd = smem_d + c.rest_o + (seq & 1u) * (c.stage_bytes >> 3);
@@ -651,14 +662,20 @@ struct DevOps {
         }
         double psi_j = 0.0, Wpsi = 0.0, deg = 0.0;
         if (c.car) {
-          psi_j = ringp[j & (4 * kTile - 1)];
           deg = (double)(kraw >> 24);
           // ELL entries are ring positions (neighbour id & (4T-1)); missing neighbours point at the
           // always-zero cell ring[4T], so the gather is branch-free
           const unsigned short *el = reinterpret_cast<const unsigned short *>(ri + 2 * kTile) + tid;
+          unsigned short pos[kMaxEll];
+#pragma unroll
+          for (int w = 0; w < kMaxEll; ++w) pos[w] = (w < c.ell_w) ? el[w * kTile] : (unsigned short)(4 * kTile);
+          // split barrier: every thread announced its part of ring(k+1) right after drifting it; only now,
+          // with the independent work above already issued, do we need all of them
+          if (k + 1 < NT) mbar_wait(c.mbar + 5 + ((seq + 1u) & 1u), ((seq + 1u) >> 1) & 1u);
+          psi_j = ringp[j & (4 * kTile - 1)];
 #pragma unroll
           for (int w = 0; w < kMaxEll; ++w)
-            if (w < c.ell_w) Wpsi += ringp[el[w * kTile]];
+            if (w < c.ell_w) Wpsi += ringp[pos[w]];
           ll += psi_j;
         }
         ll += sig03 * eps_j;
@@ -726,6 +743,7 @@ struct DevOps {
           if (merge0) rho_out[c.o_psi + j] = 0.0;
         }
       }
+      mbar_arrive(c.mbar + 7 + (seq & 1u));  // this thread no longer reads the staged inputs of tile k
 #pragma unroll
       for (int i = 0; i < KP; ++i) e[i] *= gj;
       add_bins<KP>(c.bins_o, e, bin);
