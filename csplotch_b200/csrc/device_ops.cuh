@@ -302,11 +302,12 @@ struct DevOps {
   __device__ void finish(const Scalars &sc, double a_lp, double a_ng, double a_qD, double a_qW, double a_dth,
                          double a_kin, double a_g2, double tails, double *dq, double *dg, double *dp, double eps,
                          double *V_out, double *K_out, bool *finite_out, const double *sp = nullptr,
-                         double *rho_out = nullptr, double a_pp = 0.0, double *pp_out = nullptr) {
+                         double *rho_out = nullptr, double a_pp = 0.0, double *pp_out = nullptr,
+                         bool eig_done = false, double a_ldet = 0.0, double a_dldet = 0.0) {
     const int tid = threadIdx.x;
-    // log-determinant term of the CAR prior over the distinct eigenvalues
-    double a_ldet = 0, a_dldet = 0;
-    if (m.car) {
+    // log-determinant term of the CAR prior over the distinct eigenvalues (the tiled pass folds it into
+    // its tile loop, where it is independent work that fills stall slots)
+    if (m.car && !eig_done) {
       for (int i = tid; i < m.n_eig; i += kBlock) {
         const double lam = m.eigu[i], mult = m.eigm[i];
         const double x = sc.a * lam;
@@ -555,18 +556,42 @@ struct DevOps {
       if (lane_owns_bin<KP>(lane) && b < KT) atomicAdd(&bins[b0 * KT + b], v[0]);
       return;
     }
-    unsigned remaining = __ballot_sync(0xffffffffu, bin_l >= 0);
-    while (remaining) {
-      const int leader = __ffs(remaining) - 1;
-      const int kk = __shfl_sync(0xffffffffu, bin_l, leader);
-      const bool mine = bin_l == kk;
-      double w[KP];
+    if (KP <= 2) {
+      // several bins in this warp (small ST tissues: ~6 spots per bin): segmented inclusive scan over the
+      // runs of equal bin; the last lane of every run adds the run total.  Exact for any sequence of bins
+      // (a bin that re-appears simply contributes two partial sums).
+      const int prev = __shfl_up_sync(0xffffffffu, bin_l, 1);
+      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || bin_l != prev);
+      const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+      const bool is_tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
 #pragma unroll
-      for (int i = 0; i < KP; ++i) w[i] = mine ? v[i] : 0.0;
-      warp_transpose_sum<KP>(w);
-      const int b = bin_of_lane<KP>(lane);
-      if (lane_owns_bin<KP>(lane) && b < KT) atomicAdd(&bins[kk * KT + b], w[0]);
-      remaining &= ~__ballot_sync(0xffffffffu, mine);
+      for (int i = 0; i < KP; ++i) {
+        if (i < KT) {
+          double sacc = v[i];
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, sacc, off);
+            if (lane - off >= seg_start) sacc += t;
+          }
+          if (is_tail && bin_l >= 0) atomicAdd(&bins[bin_l * KT + i], sacc);
+        }
+      }
+    } else {
+      // compositional models: a bin boundary inside a warp is rare (one tile in ~13 at c3); one transposed
+      // reduction per distinct bin keeps this path small enough not to cost the main loop registers
+      unsigned remaining = __ballot_sync(0xffffffffu, bin_l >= 0);
+      while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int kk = __shfl_sync(0xffffffffu, bin_l, leader);
+        const bool mine = bin_l == kk;
+        double w[KP];
+#pragma unroll
+        for (int i = 0; i < KP; ++i) w[i] = mine ? v[i] : 0.0;
+        warp_transpose_sum<KP>(w);
+        const int b = bin_of_lane<KP>(lane);
+        if (lane_owns_bin<KP>(lane) && b < KT) atomicAdd(&bins[kk * KT + b], w[0]);
+        remaining &= ~__ballot_sync(0xffffffffu, mine);
+      }
     }
   }
 
@@ -609,7 +634,13 @@ struct DevOps {
     const double theta = sc.theta, om_theta = 1.0 - sc.theta, tau = sc.tau, a_car = sc.a;
     const double half_eps = 0.5 * eps;
     double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0, a_pp = 0;
+    double a_ldet = 0, a_dldet = 0;
     const bool merge0 = LEAP && rho_out != nullptr;
+    // the non-compositional kernels have registers to spare and few tiles per evaluation: they fold the
+    // eigenvalue term into the tile loop; the compositional ones (register-critical loop) leave it to finish()
+    constexpr bool kEigInLoop = KT <= 2;
+    const int n_eig = kEigInLoop ? m.n_eig : 0;
+    const double *eigu = m.eigu, *eigm = m.eigm;
 
     if (c.car) {
       drift_tile<LEAP>(c, 0, eps);
@@ -626,6 +657,16 @@ struct DevOps {
         for (int i = 0; i < KP; ++i) e[i] = (i < KT) ? __ldg(Ej + (size_t)i * kTile) : 0.0;
       } else {
         e[0] = 1.0;
+      }
+      if (kEigInLoop && c.car) {
+        // one distinct eigenvalue of the CAR precision per thread and tile: sum_i mult_i log1m(a lambda_i)
+        const int ei = k * kTile + tid;
+        if (ei < n_eig) {
+          const double lam = __ldg(eigu + ei), mult = __ldg(eigm + ei);
+          const double x = a_car * lam;
+          a_ldet += mult * log1p(-x);
+          a_dldet += mult * (-lam / (1.0 - x));
+        }
       }
       if (c.car && k + 1 < NT) drift_tile<LEAP>(c, k + 1, eps);
       const uint32_t seq = c.seq0 + (uint32_t)k;
@@ -752,7 +793,7 @@ struct DevOps {
     const long long t_fin = clock64();
     // the zi-only part of d/dtheta was accumulated as (1 - e^{-mu}) / s; finish() expects it in a_dth
     finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out, sp, rho_out,
-                 a_pp, pp_out);
+                 a_pp, pp_out, kEigInLoop, a_ldet, a_dldet);
     cyc_pro += t_loop - t_begin;
     cyc_fin += clock64() - t_fin;
   }
