@@ -200,6 +200,12 @@ __global__ void k_summ_finalize(const double *__restrict__ summ, const ChainScal
 template <int KT>
 constexpr int kCtasPerSm = KT <= 2 ? 3 : 2;
 static int ctas_per_sm(int kt) { return kt <= 2 ? 3 : 2; }
+__device__ __forceinline__ void stage_model(DevModel &dst, const DevModel &src) {
+  const int n = (int)(sizeof(DevModel) / sizeof(int));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) reinterpret_cast<int *>(&dst)[i] = reinterpret_cast<const int *>(&src)[i];
+  __syncthreads();
+}
+
 // dynamic shared memory: B[nbeta] | adjB[nbeta] | red | mbar[9] | tdesc | ring[4T] | psi slots | rest slots
 template <int KT>
 __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, double *smem) {
@@ -231,10 +237,15 @@ __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, do
 
 template <int KT>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
-k_lpgrad(const __grid_constant__ DevModel m, const int *__restrict__ counts, const double *__restrict__ pm,
+k_lpgrad(const __grid_constant__ DevModel m_in, const int *__restrict__ counts, const double *__restrict__ pm,
          const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz, int G,
          const double *__restrict__ theta_int, const int *__restrict__ gene_of, int Bn, double *lp_out,
          double *grad_int, int jacobian) {
+  // the model descriptor is read all over the per-evaluation prologue / epilogue: a shared-memory copy turns
+  // those dependent generic loads from the parameter bank into LDS
+  __shared__ DevModel s_model;
+  stage_model(s_model, m_in);
+  const DevModel &m = s_model;
   DevOps<KT> ops(m);
   bind_smem(ops, m, smem_d);
   ops.jacobian = jacobian;
@@ -263,10 +274,15 @@ __global__ void k_negate(double *v, size_t n) {
 
 template <int KT>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
-k_leapfrog_fixed(const __grid_constant__ DevModel m, const int *__restrict__ counts, const double *__restrict__ pm,
+k_leapfrog_fixed(const __grid_constant__ DevModel m_in, const int *__restrict__ counts, const double *__restrict__ pm,
                  const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz,
                  int G, double *q, double *p, double *g, const double *__restrict__ minv,
                  const int *__restrict__ gene_of, int Bn, double eps, int n_steps, double *H_out) {
+  // the model descriptor is read all over the per-evaluation prologue / epilogue: a shared-memory copy turns
+  // those dependent generic loads from the parameter bank into LDS
+  __shared__ DevModel s_model;
+  stage_model(s_model, m_in);
+  const DevModel &m = s_model;
   DevOps<KT> ops(m);
   bind_smem(ops, m, smem_d);
   ops.jacobian = 1;
@@ -297,10 +313,15 @@ k_leapfrog_fixed(const __grid_constant__ DevModel m, const int *__restrict__ cou
 
 template <int KT>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
-k_nuts_advance(const __grid_constant__ DevModel m, const __grid_constant__ SamplerDev s, int n_iter) {
+k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ SamplerDev s, int n_iter) {
   __shared__ int s_work;
-  const size_t Di = m.Di;
+  const size_t Di = m_in.Di;
   double *ws = s.ws + (size_t)blockIdx.x * (size_t)(kPoolVecs + 6) * Di;
+  // the model descriptor is read all over the per-evaluation prologue / epilogue: a shared-memory copy turns
+  // those dependent generic loads from the parameter bank into LDS
+  __shared__ DevModel s_model;
+  stage_model(s_model, m_in);
+  const DevModel &m = s_model;
   DevOps<KT> ops(m);
   bind_smem(ops, m, smem_d);
   ops.jacobian = 1;
@@ -1095,9 +1116,14 @@ extern "C" int32_t csplotch_sampler_get_spot_summaries(csplotch_sampler *s, doub
 // evaluated on the device through the same load_small + spot loop as the sampler.
 template <int KT>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
-k_write_array(const __grid_constant__ DevModel m, const double *__restrict__ pm, const double *__restrict__ ps, int G,
+k_write_array(const __grid_constant__ DevModel m_in, const double *__restrict__ pm, const double *__restrict__ ps, int G,
               const double *__restrict__ theta_int, const int *__restrict__ gene_of, const int *__restrict__ perm,
               int Bn, double *out, int n_out) {
+  // the model descriptor is read all over the per-evaluation prologue / epilogue: a shared-memory copy turns
+  // those dependent generic loads from the parameter bank into LDS
+  __shared__ DevModel s_model;
+  stage_model(s_model, m_in);
+  const DevModel &m = s_model;
   DevOps<KT> ops(m);
   bind_smem(ops, m, smem_d);
   ops.jacobian = 0;
