@@ -128,6 +128,16 @@ def main(argv=None):
         a.device = int(os.environ.get("LOCAL_RANK", str(rank)))
         if not gene_ids:
             return 0
+    # genes resident at once: bounded by device memory.  Per gene: 4 D-vectors + 6 N summary doubles per
+    # chain, and (CSV mode only) every sampling draw of the full unconstrained vector.
+    try:
+        head = rdump.read_rdump(data_path(a.d, gene_ids[0]), keys=("N_spots", "car"))
+        n_spots = int(np.sum(head["N_spots"]))
+        dim = (2 if int(head.get("car", 1)) else 1) * n_spots + 4096
+        per_gene = a.c * 8 * (4 * dim + 6 * n_spots + (0 if a.s else a.n * dim))
+        a.batch = max(1, min(a.batch, int(float(os.environ.get("CSPLOTCH_MEM_GB", "60")) * 1e9 // per_gene)))
+    except (OSError, KeyError):
+        pass  # missing first file: the per-run loader reports it
     # contiguous runs keep gene_id0 + i == gene id (the RNG stream is keyed by the gene index)
     runs = shard.contiguous_runs(gene_ids, a.batch)
     rc = 0

@@ -38,19 +38,26 @@ while True:
 wall = time.time() - t0
 cnt = s.counters()
 ex = s.extract_small()
-keys = [k for k in ex if k.startswith("beta_level") or k in ("tau", "a", "sigma", "sigma_level_2", "sigma_level_3", "theta")]
-ess_min, rhat_max = [], []
+bkeys = [k for k in ex if k.startswith("beta_level")]
+skeys = [k for k in ("tau", "a", "sigma", "sigma_level_2", "sigma_level_3", "theta") if k in ex]
+ess_min, rhat_max, ess_beta, rhat_beta = [], [], [], []
 for g in range(min(G, n_eval)):
-    cols = np.concatenate([ex[k][g].reshape(4 * n, -1) for k in keys], axis=1).reshape(4, n, -1)
-    e, r = dg.summarize(cols)
-    ess_min.append(e); rhat_max.append(r)
-ess_min, rhat_max = np.array(ess_min), np.array(rhat_max)
+    cb = np.concatenate([ex[k][g].reshape(4 * n, -1) for k in bkeys], axis=1).reshape(4, n, -1)
+    cs = np.concatenate([ex[k][g].reshape(4 * n, -1) for k in skeys], axis=1).reshape(4, n, -1)
+    eb, rb = dg.summarize(cb)
+    es, rs = dg.summarize(cs)
+    ess_beta.append(eb); rhat_beta.append(rb)
+    ess_min.append(min(eb, es)); rhat_max.append(max(rb, rs))
+ess_min, rhat_max, ess_beta, rhat_beta = map(np.array, (ess_min, rhat_max, ess_beta, rhat_beta))
 diag = ex["diag"]
 res = dict(shape=which, family=family, genes=G, chains=4, num_warmup=n, num_samples=n, device_seconds=ms * 1e-3, wall_seconds=wall,
            grad_evals=cnt["n_grad"], grad_evals_per_s=cnt["n_grad"] / (ms * 1e-3), genes_per_hour=G / (ms * 1e-3) * 3600,
            genes_evaluated_for_ess=int(len(ess_min)), frac_genes_ess_ge_400=float((ess_min >= 400).mean()),
            median_min_bulk_ess=float(np.median(ess_min)), genes_per_hour_to_ess400=float(G / (ms * 1e-3) * 3600 * (ess_min >= 400).mean()),
            median_max_rhat=float(np.median(rhat_max)), frac_rhat_lt_1_01=float((rhat_max < 1.01).mean()),
+           beta_only=dict(median_min_bulk_ess=float(np.median(ess_beta)), frac_genes_ess_ge_400=float((ess_beta >= 400).mean()),
+                          genes_per_hour_to_ess400=float(G / (ms * 1e-3) * 3600 * (ess_beta >= 400).mean()),
+                          median_max_rhat=float(np.median(rhat_beta)), frac_rhat_lt_1_01=float((rhat_beta < 1.01).mean())),
            mean_treedepth=float(diag[..., 3].mean()), mean_n_leapfrog=float(diag[..., 4].mean()),
            divergent_frac=float(diag[..., 5].mean()), mean_accept_stat=float(diag[..., 1].mean()),
            failed_chains=int((s.status()[0] != 0).sum()))
