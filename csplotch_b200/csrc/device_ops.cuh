@@ -69,8 +69,21 @@ extern __shared__ __align__(16) double smem_d[];
 
 struct Scalars {
   double tau, a, sigma, s2, s3, theta;
-  double jac;  // sum of log-Jacobians
+  double jac;          // sum of log-Jacobians
+  double log_tau;      // = the unconstrained value itself
+  double log1m_theta;  // log(1 - theta), shared with the log-Jacobian of theta
 };
+
+// x = inv_logit(u) together with log x and log(1 - x) from ONE exp and ONE log1p
+// (log_inv_logit(u) = min(u,0) - log1p(e^{-|u|}), log1m_inv_logit(u) = min(-u,0) - log1p(e^{-|u|}))
+__device__ __forceinline__ void logit_triple(double u, double &x, double &log_x, double &log1m_x) {
+  const double e = exp(-fabs(u));
+  const double l = log1p(e);
+  const double r = 1.0 / (1.0 + e);
+  x = u >= 0 ? r : e * r;
+  log_x = fmin(u, 0.0) - l;
+  log1m_x = fmin(-u, 0.0) - l;
+}
 
 __device__ __forceinline__ double inv_logit_d(double u) {
   if (u < 0) {
@@ -234,25 +247,30 @@ struct DevOps {
     const double *ss = sb + m.nbeta;
     sc.tau = sc.a = sc.s2 = sc.s3 = sc.theta = 0.0;
     double jac = 0.0;
+    // all (<= 6) unconstrained scalars in ONE batch of independent loads: fetched one by one inside the
+    // branches below, each paid a full L2 round trip before its exp()
+    const int last = m.nscal - 1;
+    const double u_tau = ss[max(0, min(m.s_tau, last))], u_a = ss[max(0, min(m.s_a, last))];
+    const double u_sigma = ss[m.s_sigma], u_s2 = ss[max(0, min(m.s_s2, last))];
+    const double u_s3 = ss[max(0, min(m.s_s3, last))], u_theta = ss[max(0, min(m.s_theta, last))];
+    sc.log_tau = 0.0;
+    sc.log1m_theta = 0.0;
     if (m.car) {
-      double u = ss[m.s_tau];
-      sc.tau = exp(u);
-      jac += u;
-      u = ss[m.s_a];
-      sc.a = inv_logit_d(u);
-      jac += log_inv_logit_d(u) + log1m_inv_logit_d(u);
+      sc.tau = exp(u_tau);
+      sc.log_tau = u_tau;
+      jac += u_tau;
+      double la, l1a;
+      logit_triple(u_a, sc.a, la, l1a);
+      jac += la + l1a;
     }
-    {
-      const double u = ss[m.s_sigma];
-      sc.sigma = exp(u);
-      jac += u;
-    }
-    if (m.L2) { const double u = ss[m.s_s2]; sc.s2 = exp(u); jac += u; }
-    if (m.L3) { const double u = ss[m.s_s3]; sc.s3 = exp(u); jac += u; }
+    sc.sigma = exp(u_sigma);
+    jac += u_sigma;
+    if (m.L2) { sc.s2 = exp(u_s2); jac += u_s2; }
+    if (m.L3) { sc.s3 = exp(u_s3); jac += u_s3; }
     if (m.zi) {
-      const double u = ss[m.s_theta];
-      sc.theta = inv_logit_d(u);
-      jac += log_inv_logit_d(u) + log1m_inv_logit_d(u);
+      double lt;
+      logit_triple(u_theta, sc.theta, lt, sc.log1m_theta);
+      jac += lt + sc.log1m_theta;
     }
     sc.jac = jacobian ? jac : 0.0;
     const int CK = m.C * m.K;
@@ -305,6 +323,18 @@ struct DevOps {
                          double *rho_out = nullptr, double a_pp = 0.0, double *pp_out = nullptr,
                          bool eig_done = false, double a_ldet = 0.0, double a_dldet = 0.0) {
     const int tid = threadIdx.x;
+    // momenta / metric entries of the (<= 6) scalars: one batch of independent loads issued now, so that
+    // their latency overlaps the reductions below instead of stalling the scalar epilogue
+    const int so = m.o_small + m.nbeta;
+    const int sidx[6] = {m.s_tau, m.s_a, m.s_sigma, m.s_s2, m.s_s3, m.s_theta};
+    double ph_s[6], mi_s[6], po_s[6];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      const int e = so + max(0, sidx[s]);
+      ph_s[s] = LEAP ? dp[e] : 0.0;
+      mi_s[s] = LEAP ? minv[e] : 0.0;
+      po_s[s] = (LEAP && rho_out) ? sp[e] : 0.0;
+    }
     // log-determinant term of the CAR prior over the distinct eigenvalues (the tiled pass folds it into
     // its tile loop, where it is independent work that fills stall slots)
     if (m.car && !eig_done) {
@@ -373,13 +403,13 @@ struct DevOps {
     double lp = r1[0] + sc.jac;
     double kin = r1[5] + r2[2];
     double g2 = r1[8] + r2[3];
-    const int so = m.o_small + m.nbeta;
     double gu_tau = 0, gu_a = 0, gu_sigma, gu_s2 = 0, gu_s3 = 0, gu_theta = 0;
     if (m.car) {
       const double Q = r1[2] - sc.a * r1[3];
-      lp += -2.0 * log(sc.tau) - 1.0 / sc.tau;
-      lp += 0.5 * ((double)m.N * log(sc.tau) + r1[6] - sc.tau * Q);
-      const double d_tau = -2.0 / sc.tau + 1.0 / (sc.tau * sc.tau) + 0.5 * ((double)m.N / sc.tau - Q);
+      const double inv_tau = 1.0 / sc.tau;
+      lp += -2.0 * sc.log_tau - inv_tau;
+      lp += 0.5 * ((double)m.N * sc.log_tau + r1[6] - sc.tau * Q);
+      const double d_tau = -2.0 * inv_tau + inv_tau * inv_tau + 0.5 * ((double)m.N * inv_tau - Q);
       const double d_a = 0.5 * (r1[7] + sc.tau * r1[3]);
       gu_tau = sc.tau * d_tau + (jacobian ? 1.0 : 0.0);
       gu_a = sc.a * (1.0 - sc.a) * d_a + (jacobian ? (1.0 - 2.0 * sc.a) : 0.0);
@@ -395,21 +425,17 @@ struct DevOps {
       gu_theta = sc.theta * (1.0 - sc.theta) * d_theta + (jacobian ? (1.0 - 2.0 * sc.theta) : 0.0);
     }
     // read phase (all threads) then write phase (thread 0) of the scalar momenta
-    double pn_s[6] = {0, 0, 0, 0, 0, 0}, po_s[6] = {0, 0, 0, 0, 0, 0};
+    double pn_s[6] = {0, 0, 0, 0, 0, 0};
     double pp = r2[4];
     const double gu[6] = {gu_tau, gu_a, gu_sigma, gu_s2, gu_s3, gu_theta};
-    const int sidx[6] = {m.s_tau, m.s_a, m.s_sigma, m.s_s2, m.s_s3, m.s_theta};
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       if (sidx[s] >= 0) {
         g2 += gu[s] * gu[s];
         if (LEAP) {
-          pn_s[s] = dp[so + sidx[s]] + 0.5 * eps * gu[s];
-          kin += minv[so + sidx[s]] * pn_s[s] * pn_s[s];
-          if (rho_out) {
-            po_s[s] = sp[so + sidx[s]];
-            pp += minv[so + sidx[s]] * po_s[s] * pn_s[s];
-          }
+          pn_s[s] = ph_s[s] + 0.5 * eps * gu[s];
+          kin += mi_s[s] * pn_s[s] * pn_s[s];
+          if (rho_out) pp += mi_s[s] * po_s[s] * pn_s[s];
         }
       }
     }
@@ -608,7 +634,7 @@ struct DevOps {
     const bool write_q = LEAP || dq != sq;
     // generic-proxy writes of earlier passes (q, p, g of this chain) must be visible to the async proxy
     // (TMA) that is about to read them; the barrier also publishes the descriptor table
-    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncthreads();
     // the first tiles start streaming while the small block is prepared
     if (tid < 32) {
@@ -629,7 +655,7 @@ struct DevOps {
     Scalars sc;
     load_small(dq, sc);
     for (int idx = tid; idx < m.nbeta; idx += kBlock) adjB[idx] = 0.0;
-    const double tails = c.zi ? log1p(-sc.theta) : 0.0;
+    const double tails = sc.log1m_theta;
     const double sig03 = 0.3 * sc.sigma;
     const double theta = sc.theta, om_theta = 1.0 - sc.theta, tau = sc.tau, a_car = sc.a;
     const double half_eps = 0.5 * eps;
