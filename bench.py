@@ -42,7 +42,7 @@ WORKLOADS = {
                            "D=5016, all 11313 genes x 4 chains"),
     "c3": ("c3", 592, 1, "c3: synthetic Visium 24x4992 spots, comp_splotch_stan_model 3-level ZIP+CAR K=10, "
                          "D=242142, gene slice x 4 chains"),
-    "c4": ("c4", 148, 1, "c4: synthetic Visium-HD 4x317^2 bins, splotch_stan_model_csr 2-level ZIP+CAR, D=803989, "
+    "c4": ("c4", 296, 1, "c4: synthetic Visium-HD 4x317^2 bins, splotch_stan_model_csr 2-level ZIP+CAR, D=803989, "
                          "gene slice x 4 chains"),
     "c5": ("c5", 592, 1, "c5: c3 covariates, 32768-gene sweep sharded over the GPUs (slice per GPU) x 4 chains"),
 }

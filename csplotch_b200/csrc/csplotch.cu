@@ -90,10 +90,11 @@ struct csplotch_batch {
 struct SamplerDev {
   ChainScalars *cs;
   double *q_cur, *minv, *wm, *wm2;  // [W][Di]
-  double *ws;                       // [slots][kPoolVecs + 6][Di]
+  double *ws;                       // [slots][pool_vecs + 6][Di]
   double *diag, *small, *theta, *summ;
   int *queue;
   int W, num_chains, n_slots, have_init;
+  int pool_vecs;                    // 3 * max_depth + 8 D-vectors of momenta / rho sums per slot
   uint32_t gene_id0;
   NutsConfig cfg;
   const int *counts;
@@ -206,7 +207,7 @@ __device__ __forceinline__ void stage_model(DevModel &dst, const DevModel &src) 
   __syncthreads();
 }
 
-// dynamic shared memory: B[nbeta] | adjB[nbeta] | red | mbar[9] | tdesc | ring[4T] | psi slots | rest slots
+// dynamic shared memory: B[nbeta] | adjB[nbeta] | red | mbar[10] | tdesc | ring[4T or 8T] + zero cell | psi slots | rest slots
 template <int KT>
 __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, double *smem) {
   ops.B = smem;
@@ -217,19 +218,20 @@ __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, do
   p += 10;
   ops.tdesc = reinterpret_cast<TmaDesc *>(p);
   p += (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 2;
+  const int ring_tiles = m.look == 1 ? 4 : 8;
   ops.ring = p;
-  p += 4 * kTile + 2;  // + the always-zero cell missing neighbours point at
+  p += ring_tiles * kTile + 2;  // + the always-zero cell missing neighbours point at
   ops.psi_st = p;
-  p += 12 * kTile;
+  p += (m.look + 2) * 4 * kTile;
   ops.rest_st = reinterpret_cast<unsigned char *>(p);
   ops.tile_seq = 0;
   if (m.tiled) {
     if (threadIdx.x == 0) {
-      for (int i = 0; i < 5; ++i) mbar_init(ops.mbar + i, 1);
-      for (int i = 5; i < 9; ++i) mbar_init(ops.mbar + i, kBlock);
+      for (int i = 0; i < 6; ++i) mbar_init(ops.mbar + i, 1);
+      for (int i = 6; i < 10; ++i) mbar_init(ops.mbar + i, kBlock);
       mbar_fence_init();
-      ops.ring[4 * kTile] = 0.0;
-      ops.ring[4 * kTile + 1] = 0.0;
+      ops.ring[ring_tiles * kTile] = 0.0;
+      ops.ring[ring_tiles * kTile + 1] = 0.0;
     }
     __syncthreads();
   }
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
 k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ SamplerDev s, int n_iter) {
   __shared__ int s_work;
   const size_t Di = m_in.Di;
-  double *ws = s.ws + (size_t)blockIdx.x * (size_t)(kPoolVecs + 6) * Di;
+  double *ws = s.ws + (size_t)blockIdx.x * (size_t)(s.pool_vecs + 6) * Di;
   // the model descriptor is read all over the per-evaluation prologue / epilogue: a shared-memory copy turns
   // those dependent generic loads from the parameter bank into LDS
   __shared__ DevModel s_model;
@@ -339,7 +341,7 @@ k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ Sa
     ops.gn.nnz = s.nnz[g];
     ops.key = RngKey{s.cfg.seed, (uint32_t)c + 1u, s.gene_id0 + (uint32_t)g};
     ops.pool = ws;
-    ops.zq[0] = ws + (size_t)kPoolVecs * Di;
+    ops.zq[0] = ws + (size_t)s.pool_vecs * Di;
     ops.zg[0] = ops.zq[0] + Di;
     ops.zq[1] = ops.zg[0] + Di;
     ops.zg[1] = ops.zq[1] + Di;
@@ -503,20 +505,24 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   // same or an adjacent tile of kTile spots.  Try the given order first (row-major arrays already satisfy
   // it); otherwise relabel each connected component breadth-first (Cuthill-McKee), which bounds the
   // bandwidth by the width of the tissue; if that still does not fit the generic kernel is used.
-  auto fits = [&](const std::vector<int> &perm) {
-    if (!car) return true;
+  // smallest neighbour reach in tiles (1 or 2) under which `perm` tiles, 0 if it does not
+  auto reach = [&](const std::vector<int> &perm) {
+    if (!car) return 1;
     std::vector<int> inv(N);
     for (int j = 0; j < N; ++j) inv[perm[j]] = j;
+    int r = 1;
     for (int j = 0; j < N; ++j) {
       const auto &a = adj0[perm[j]];
-      if ((int)a.size() > kMaxEll) return false;
+      if ((int)a.size() > kMaxEll) return 0;
       for (int nb : a) {
-        const int dt = inv[nb] / kTile - j / kTile;
-        if (dt > 1 || dt < -1) return false;
+        const int dt = std::abs(inv[nb] / kTile - j / kTile);
+        if (dt > 2) return 0;
+        r = std::max(r, dt);
       }
     }
-    return true;
+    return r;
   };
+  auto fits = [&](const std::vector<int> &perm) { return reach(perm) != 0; };
   m->perm.resize(N);
   for (int j = 0; j < N; ++j) m->perm[j] = j;
   bool tiled = fits(m->perm);
@@ -564,7 +570,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     });
     // tissues must stay contiguous for this to make sense: perm lists whole tissues one after another in
     // both the given and the breadth-first order (components never straddle tissues)
-    if (cand != m->perm && fits(cand)) m->perm = cand;
+    if (cand != m->perm && reach(cand) != 0 && reach(cand) <= reach(m->perm)) m->perm = cand;
   }
   if (force && std::string(force) == "generic") tiled = false;
   std::vector<int> inv(N);
@@ -573,10 +579,12 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   if (car)
     for (int i = 0; i < N; ++i) ell_w = std::max(ell_w, (int)adj0[i].size());
   dm.tiled = tiled ? 1 : 0;
+  dm.look = tiled ? std::max(1, reach(m->perm)) : 1;
+  if (dm.look == 2 && kt > 2) { tiled = false; dm.tiled = 0; dm.look = 1; }  // reach 2 is built for the non-compositional kernels only
   dm.ell_w = (car && tiled) ? ell_w : 0;
   dm.stage_bytes = (5 * kTile) * (int)sizeof(double) + 2 * kTile * (int)sizeof(int) + ((dm.ell_w + 1) / 2 * 2) * kTile * (int)sizeof(unsigned short);
   m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 10) * sizeof(double) + (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 16;
-  if (tiled) m->smem_bytes += ((size_t)(4 + 12) * kTile + 2) * sizeof(double) + 2 * (size_t)dm.stage_bytes;
+  if (tiled) m->smem_bytes += ((size_t)((dm.look == 1 ? 4 : 8) + 4 * (dm.look + 2)) * kTile + 2) * sizeof(double) + 2 * (size_t)dm.stage_bytes;
   if (m->smem_bytes > 220 * 1024) {
     delete m;
     return fail(CSPLOTCH_E_UNSUPPORTED, "beta table (L*C*K) too large for shared memory");
@@ -620,7 +628,8 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   std::vector<unsigned short> ell;
   std::vector<double> eigu, eigm;
   if (car) {
-    if (tiled) ell.assign((size_t)dm.NT * dm.ell_w * kTile, (unsigned short)(4 * kTile));
+    const int ring_n = (dm.look == 1 ? 4 : 8) * kTile;
+    if (tiled) ell.assign((size_t)dm.NT * dm.ell_w * kTile, (unsigned short)ring_n);
     for (int i = 0; i < N; ++i) {
       std::vector<int> a;
       for (int nb : adj0[m->perm[i]]) a.push_back(inv[nb]);
@@ -629,7 +638,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
       col.insert(col.end(), a.begin(), a.end());
       if (tiled)
         for (size_t w = 0; w < a.size(); ++w)
-          ell[((size_t)(i / kTile) * dm.ell_w + w) * kTile + (i % kTile)] = (unsigned short)(a[w] & (4 * kTile - 1));
+          ell[((size_t)(i / kTile) * dm.ell_w + w) * kTile + (i % kTile)] = (unsigned short)(a[w] & (ring_n - 1));
     }
     // distinct eigenvalues with multiplicity (exact duplicates only; c3 has 24 identical arrays)
     std::map<double, double> mult;
@@ -905,8 +914,25 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
                       cfg->init_buffer, cfg->term_buffer, cfg->window, cfg->init_radius, cfg->stepsize, cfg->seed};
   sd.counts = b->counts; sd.pm = b->pm; sd.ps = b->ps; sd.lgam = b->lgam; sd.nnz = b->nnz;
   s->grid = std::min(W, sm_count() * ctas_per_sm(m->kt));
-  sd.n_slots = s->grid;
+  sd.pool_vecs = 3 * cfg->max_depth + 8;
   const size_t Di = dm.Di, ns = (size_t)cfg->num_samples;
+  // resident CTAs are also bounded by HBM: every CTA slot owns pool_vecs + 6 D-vectors of workspace
+  // (c4: 284 MB).  Per-chain state and outputs come first; the slots share 90 % of what is left.
+  {
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_chain = sizeof(ChainScalars) + (4 * Di + ns * (7 + dm.nsmall_true) + 6 * (size_t)dm.N +
+                                                     (cfg->keep_draws ? ns * (size_t)dm.D : 0)) * sizeof(double);
+    const size_t need = (size_t)W * per_chain;
+    const size_t per_slot = (size_t)(sd.pool_vecs + 6) * Di * sizeof(double);
+    if (need + per_slot > free_b) {
+      delete s;
+      return fail(CSPLOTCH_E_NOMEM, "not enough device memory for this many gene-chains: sample fewer genes per batch");
+    }
+    const size_t max_slots = (size_t)(0.9 * (double)(free_b - need)) / per_slot;
+    s->grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->grid, max_slots));
+  }
+  sd.n_slots = s->grid;
   cudaError_t e = cudaSuccess;
   auto A = [&](auto **p, size_t n) { if (e == cudaSuccess) e = s->buf.alloc(p, n); };
   A(&sd.cs, (size_t)W);
@@ -914,7 +940,7 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   A(&sd.minv, (size_t)W * Di);
   A(&sd.wm, (size_t)W * Di);
   A(&sd.wm2, (size_t)W * Di);
-  A(&sd.ws, (size_t)sd.n_slots * (kPoolVecs + 6) * Di);
+  A(&sd.ws, (size_t)sd.n_slots * (sd.pool_vecs + 6) * Di);
   A(&sd.diag, (size_t)W * ns * 7);
   A(&sd.small, (size_t)W * ns * dm.nsmall_true);
   A(&sd.summ, (size_t)W * 6 * dm.N);
@@ -930,7 +956,7 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   CU_TRY(cudaEventCreate(&s->ev1));
   CU_TRY(cudaMemsetAsync(sd.cs, 0, (size_t)W * sizeof(ChainScalars), s->stream));
   CU_TRY(cudaMemsetAsync(sd.q_cur, 0, (size_t)W * Di * sizeof(double), s->stream));
-  CU_TRY(cudaMemsetAsync(sd.ws, 0, (size_t)sd.n_slots * (kPoolVecs + 6) * Di * sizeof(double), s->stream));
+  CU_TRY(cudaMemsetAsync(sd.ws, 0, (size_t)sd.n_slots * (sd.pool_vecs + 6) * Di * sizeof(double), s->stream));
   CU_TRY(cudaMemsetAsync(sd.summ, 0, (size_t)W * 6 * dm.N * sizeof(double), s->stream));
   CU_TRY(cudaMemsetAsync(sd.diag, 0, (size_t)W * ns * 7 * sizeof(double), s->stream));
   CU_TRY(cudaMemsetAsync(sd.small, 0, (size_t)W * ns * dm.nsmall_true * sizeof(double), s->stream));

@@ -39,14 +39,15 @@ struct DevModel {
   int n_eig;
   int Nc;      // row stride of the counts matrix (int32 elements) = Npad
   int NT;      // tiles of kTile spots; Npad = NT * kTile
-  int tiled;   // 1: every neighbour lies in the same or an adjacent tile and degree <= ell_w
+  int tiled;   // 1: every neighbour lies within `look` tiles and degree <= kMaxEll
+  int look;    // 1 or 2: how many tiles a neighbour may be away (Visium / ST: 1; 317-wide HD rows: 2)
   int ell_w;   // ELL width (max degree), 0 without CAR
   int stage_bytes;
   const double *lsf;     // [Npad] log(size_factors), 0 in the padding
   const int *key;        // [Npad] bits 0-23 bottom-level bin (tissue_mapping[t]-1)*C + D_j-1, bits 24-27 degree; -1 = padding
   const int *rowptr;     // [N+1] CSR of the symmetric adjacency (internal spot ids)
   const int *col;        // [2 W_n]
-  const unsigned short *ell;  // [NT][ell_w][kTile] ring positions of the neighbours (id & (4T-1)); 4T = none
+  const unsigned short *ell;  // [NT][ell_w][kTile] ring positions of the neighbours (id & rmask); rmask+1 = none
   const double *E;       // [NT][K][kTile]  (tile-major, cell type, spot-in-tile): coalesced per k
   const double *eigu;    // [n_eig] distinct eigenvalues
   const double *eigm;    // [n_eig] multiplicities
@@ -216,13 +217,13 @@ struct DevOps {
   int jacobian;
   // shared memory: B[nbeta] | adjB[nbeta] | red[kWarps*kRedMax] | mbar[kStages] | ring[4 T] | phr[2 T] | stages
   double *B, *adjB, *red;
-  uint64_t *mbar;        // [0..2] psi slot landed (TMA), [3,4] rest slot landed (TMA), [5,6] psi of a tile is in the
-                         // ring (256 arrivals), [7,8] every thread is done with a tile's staged inputs (256 arrivals)
+  uint64_t *mbar;        // [0..3] psi slot landed (TMA), [4,5] rest slot landed (TMA), [6,7] psi of a tile is in the
+                         // ring (256 arrivals), [8,9] every thread is done with a tile's staged inputs (256 arrivals)
   double *ring;          // drifted psi of tiles k-1, k, k+1 (+1 spare): ring[j & (4 T - 1)]
   double *psi_st;        // 3 slots x {q,p,g,minv}[T] of the psi block (TMA destination); tile x in slot x mod 3
   unsigned char *rest_st;  // 2 slots x stage_bytes: {q,p,g,minv}[T] of noise_raw, lsf[T], counts[T], key[T], ell[w][T]
-  uint32_t tile_seq;     // tiles consumed so far by this CTA, mod 12: psi slot seq % 3 (parity (seq / 3) & 1),
-                         // rest slot seq & 1 (parity (seq >> 1) & 1)
+  uint32_t tile_seq;     // tiles consumed so far by this CTA, mod 4 (look+2): psi slot seq % (look+2), parity
+                         // (seq / (look+2)) & 1; rest slot seq & 1, parity (seq >> 1) & 1
   TmaDesc *tdesc;        // kMaxDesc TMA stream descriptors (shared memory)
   // HBM vectors of this CTA slot / chain
   double *pool;         // kPoolVecs x Di
@@ -533,40 +534,46 @@ struct DevOps {
     }
     return c;
   }
-  // psi inputs run two tiles ahead (the drift of tile k+1 precedes the gradient of tile k, which still
-  // reads p, g, minv of its own tile) in three slots; the rest one tile ahead in two slots.  Called by
-  // every lane of warp 0 at trip k: issues psi(k+2) and rest(k+1).
+  // psi inputs run look+1 tiles ahead (the drift of tile k+look precedes the gradient of tile k, which
+  // still reads p, g, minv of its own tile) in look+2 slots; the rest one tile ahead in two slots.  Called
+  // by every lane of warp 0 at trip k: issues psi(k+look+1) and rest(k+1).
+  template <int LOOK>
   static __device__ __forceinline__ void issue_tiles(const TileCtx &c, int k) {
+    constexpr uint32_t NPS = LOOK + 2;
     const int lane = threadIdx.x;  // warp 0: lane == tid
-    if (lane == 0 && c.car && k + 2 >= 0 && k + 2 < c.NT)
-      mbar_expect_tx(c.mbar + ((c.seq0 + (uint32_t)(k + 2)) % 3u), c.psi_tx);
+    const int kp = k + LOOK + 1;  // psi tile issued at trip k
+    if (lane == 0 && c.car && kp >= 0 && kp < c.NT)
+      mbar_expect_tx(c.mbar + ((c.seq0 + (uint32_t)kp) % NPS), c.psi_tx);
     if (lane == 1 && k + 1 >= 0 && k + 1 < c.NT)
-      mbar_expect_tx(c.mbar + 3 + ((c.seq0 + (uint32_t)(k + 1)) & 1u), c.rest_tx);
+      mbar_expect_tx(c.mbar + 4 + ((c.seq0 + (uint32_t)(k + 1)) & 1u), c.rest_tx);
     __syncwarp();
     if (lane < c.n_desc) {
       const TmaDesc d = c.desc[lane];
-      const int tile = k + (d.group == 0 ? 2 : 1);
+      const int tile = d.group == 0 ? kp : k + 1;
       if (tile >= 0 && tile < c.NT) {
         const uint32_t seq = c.seq0 + (uint32_t)tile;
-        const uint32_t slot = d.group == 0 ? seq % 3u : (seq & 1u);
+        const uint32_t slot = d.group == 0 ? seq % NPS : (seq & 1u);
         unsigned char *dst = d.group == 0
                                  ? reinterpret_cast<unsigned char *>(smem_d + c.psi_o) + slot * (4 * kTile * sizeof(double))
                                  : reinterpret_cast<unsigned char *>(smem_d + c.rest_o) + (size_t)slot * c.stage_bytes;
-        bulk_g2s(dst + d.dst_off, d.src + (size_t)tile * d.tile_bytes, d.tile_bytes, c.mbar + 3 * d.group + slot);
+        bulk_g2s(dst + d.dst_off, d.src + (size_t)tile * d.tile_bytes, d.tile_bytes, c.mbar + 4 * d.group + slot);
       }
     }
   }
   // drift psi of tile k into the ring
-  template <bool LEAP>
+  template <bool LEAP, int LOOK>
   static __device__ __forceinline__ void drift_tile(const TileCtx &c, int k, double eps) {
+    constexpr uint32_t NPS = LOOK + 2;
+    constexpr int RMASK = (LOOK == 1 ? 4 : 8) * kTile - 1;
     const int t = threadIdx.x;
     const uint32_t seq = c.seq0 + (uint32_t)k;
-    mbar_wait(c.mbar + (seq % 3u), (seq / 3u) & 1u);
-    const double *d = smem_d + c.psi_o + (seq % 3u) * 4 * kTile;
+    const uint32_t ps = seq % NPS;
+    mbar_wait(c.mbar + ps, (seq / NPS) & 1u);
+    const double *d = smem_d + c.psi_o + ps * 4 * kTile;
     double qn = d[t];
     if (LEAP) qn += eps * d[3 * kTile + t] * (d[kTile + t] - 0.5 * eps * d[2 * kTile + t]);
-    smem_d[c.ring_o + ((k & 3) * kTile) + t] = qn;
-    mbar_arrive(c.mbar + 5 + (seq & 1u));  // "psi of tile k is in the ring" (256 arrivals per use)
+    smem_d[c.ring_o + ((k * kTile + t) & RMASK)] = qn;
+    mbar_arrive(c.mbar + 6 + (seq & 1u));  // "psi of tile k is in the ring" (256 arrivals per use)
   }
 
   // per-tile contribution of one warp to the bottom-level bins: G[bin][k] += sum_lanes gj * E[lane][k]
@@ -621,12 +628,14 @@ struct DevOps {
     }
   }
 
-  template <bool LEAP>
+  template <bool LEAP, int LOOK>
   __device__ __noinline__ void eval_tiled(const double *__restrict__ sq, const double *__restrict__ sg,
                                           const double *__restrict__ sp, double *dq, double *dg, double *dp,
                                           double eps, double *V_out, double *K_out, bool *finite_out,
                                           double *rho_out, double *pp_out) {
     constexpr int KP = KT <= 1 ? 1 : (KT <= 2 ? 2 : (KT <= 4 ? 4 : (KT <= 8 ? 8 : 16)));
+    constexpr uint32_t NPS = LOOK + 2;
+    constexpr int RMASK = (LOOK == 1 ? 4 : 8) * kTile - 1;
     const int tid = threadIdx.x;
     const long long t_begin = clock64();
     const TileCtx c = make_ctx<LEAP>(sq, sg, sp);
@@ -637,10 +646,8 @@ struct DevOps {
     asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncthreads();
     // the first tiles start streaming while the small block is prepared
-    if (tid < 32) {
-      issue_tiles(c, -2);
-      issue_tiles(c, -1);
-    }
+    if (tid < 32)
+      for (int k0 = -(LOOK + 1); k0 < 0; ++k0) issue_tiles<LOOK>(c, k0);  // psi(0..look), rest(0)
     // small block: half-kick + drift (or copy), then constrained scalars and beta levels
     for (int e = m.o_small + tid; e < m.Di; e += kBlock) {
       double qn = sq[e];
@@ -668,10 +675,12 @@ struct DevOps {
     const int n_eig = kEigInLoop ? m.n_eig : 0;
     const double *eigu = m.eigu, *eigm = m.eigm;
 
-    if (c.car) {
-      drift_tile<LEAP>(c, 0, eps);
-      mbar_wait(c.mbar + 5 + (c.seq0 & 1u), (c.seq0 >> 1) & 1u);  // ring(0); later tiles are awaited one ahead
-    }
+    if (c.car)
+      for (int k0 = 0; k0 < LOOK && k0 < NT; ++k0) {
+        drift_tile<LEAP, LOOK>(c, k0, eps);
+        const uint32_t sq0 = c.seq0 + (uint32_t)k0;
+        mbar_wait(c.mbar + 6 + (sq0 & 1u), (sq0 >> 1) & 1u);  // ring(0..look-1); later tiles are awaited `look` ahead
+      }
     const long long t_loop = clock64();
     for (int k = 0; k < NT; ++k) {
       // cell-type fractions of this tile straight from L2 (gene-shared, coalesced per k); issued before
@@ -694,15 +703,15 @@ struct DevOps {
           a_dldet += mult * (-lam / (1.0 - x));
         }
       }
-      if (c.car && k + 1 < NT) drift_tile<LEAP>(c, k + 1, eps);
+      if (c.car && k + LOOK < NT) drift_tile<LEAP, LOOK>(c, k + LOOK, eps);
       const uint32_t seq = c.seq0 + (uint32_t)k;
       if (tid < 32) {
         // psi(k+2) and rest(k+1) go into the slots of tile k-1: wait until every thread has released them
-        if (k > 0) mbar_wait(c.mbar + 7 + ((seq - 1u) & 1u), ((seq - 1u) >> 1) & 1u);
-        issue_tiles(c, k);
+        if (k > 0) mbar_wait(c.mbar + 8 + ((seq - 1u) & 1u), ((seq - 1u) >> 1) & 1u);
+        issue_tiles<LOOK>(c, k);
       }
-      mbar_wait(c.mbar + 3 + (seq & 1u), (seq >> 1) & 1u);
-      const double *pd = smem_d + c.psi_o + (seq % 3u) * 4 * kTile;  // q, p, g, minv of psi, tile k
+      mbar_wait(c.mbar + 4 + (seq & 1u), (seq >> 1) & 1u);
+      const double *pd = smem_d + c.psi_o + (seq % NPS) * 4 * kTile;  // q, p, g, minv of psi, tile k
       const double *rd = smem_d + c.rest_o + (seq & 1u) * (c.stage_bytes >> 3);
       const int *ri = reinterpret_cast<const int *>(rd + 5 * kTile);
       const double *ringp = smem_d + c.ring_o;
@@ -735,11 +744,14 @@ struct DevOps {
           const unsigned short *el = reinterpret_cast<const unsigned short *>(ri + 2 * kTile) + tid;
           unsigned short pos[kMaxEll];
 #pragma unroll
-          for (int w = 0; w < kMaxEll; ++w) pos[w] = (w < c.ell_w) ? el[w * kTile] : (unsigned short)(4 * kTile);
+          for (int w = 0; w < kMaxEll; ++w) pos[w] = (w < c.ell_w) ? el[w * kTile] : (unsigned short)(RMASK + 1);
           // split barrier: every thread announced its part of ring(k+1) right after drifting it; only now,
           // with the independent work above already issued, do we need all of them
-          if (k + 1 < NT) mbar_wait(c.mbar + 5 + ((seq + 1u) & 1u), ((seq + 1u) >> 1) & 1u);
-          psi_j = ringp[j & (4 * kTile - 1)];
+          if (k + LOOK < NT) {
+            const uint32_t sl = seq + (uint32_t)LOOK;
+            mbar_wait(c.mbar + 6 + (sl & 1u), (sl >> 1) & 1u);
+          }
+          psi_j = ringp[j & RMASK];
 #pragma unroll
           for (int w = 0; w < kMaxEll; ++w)
             if (w < c.ell_w) Wpsi += ringp[pos[w]];
@@ -810,12 +822,12 @@ struct DevOps {
           if (merge0) rho_out[c.o_psi + j] = 0.0;
         }
       }
-      mbar_arrive(c.mbar + 7 + (seq & 1u));  // this thread no longer reads the staged inputs of tile k
+      mbar_arrive(c.mbar + 8 + (seq & 1u));  // this thread no longer reads the staged inputs of tile k
 #pragma unroll
       for (int i = 0; i < KP; ++i) e[i] *= gj;
       add_bins<KP>(c.bins_o, e, bin);
     }
-    tile_seq = (c.seq0 + (uint32_t)NT) % 12u;
+    tile_seq = (c.seq0 + (uint32_t)NT) % (4u * NPS);
     const long long t_fin = clock64();
     // the zi-only part of d/dtheta was accumulated as (1 - e^{-mu}) / s; finish() expects it in a_dth
     finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out, sp, rho_out,
@@ -833,7 +845,9 @@ struct DevOps {
   __device__ void eval(const double *sq, const double *sg, const double *sp, double *dq, double *dg,
                        double *dp, double eps, double *V_out, double *K_out, bool *finite_out,
                        double *rho_out = nullptr, double *pp_out = nullptr) {
-    if (m.tiled) eval_tiled<LEAP>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
+    // neighbours up to two tiles away (317-wide Visium-HD rows) only for the non-compositional kernels
+    if (m.tiled && KT <= 2 && m.look == 2) eval_tiled<LEAP, (KT <= 2 ? 2 : 1)>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
+    else if (m.tiled) eval_tiled<LEAP, 1>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
     else eval_generic<LEAP>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
   }
 

@@ -154,6 +154,37 @@ def test_lp_grad_all_kernel_paths(family, order, monkeypatch):
         assert np.allclose(b.write_array(theta[i:i + 1], gene_of=[i])[0], oi.write_array(theta[i]), rtol=1e-13, atol=1e-13)
 
 
+def test_wide_rows_need_two_tile_reach():
+    """Visium-HD style: 300-wide row-major grids put the vertical neighbour 300 spots (two 256-spot tiles)
+    away; the tiled pipeline then drifts psi two tiles ahead (LOOK = 2, non-compositional kernels)."""
+    family = "splotch_stan_model_csr"
+    rng = np.random.default_rng(2)
+    h, w = 5, 300
+    p = synth.grid4_pairs(h, w)
+    n = h * w
+    shared = synth.build_shared([n, n], [p, p], [synth.car_eigenvalues(p, n)] * 2, rng.integers(1, 4, size=2 * n),
+                                [1, 2], (1, 2), [1, 1], [], np.clip(rng.lognormal(0, 0.5, 2 * n), 0.05, 8), 3, zi=1, car=1)
+    genes = synth.simulate_counts(shared, 2, 3)
+    b = _batch(shared, genes, family, gene_id0=1)
+    theta = rng.normal(0, 0.8, (2, b.model.dim))
+    lp, grad = b.log_prob_grad(theta, gene_of=[0, 1])
+    for i in range(2):
+        o = oracle.Oracle(synth.gene_dict(shared, genes, i), family)
+        lp0, g0 = o.log_prob_grad(theta[i])
+        assert abs(lp[i] - lp0) < 1e-10 * abs(lp0) and _rel(grad[i], g0) < 1e-10
+        p0 = rng.normal(0, 1, b.model.dim)
+        th, pp, H = b.leapfrog_fixed(theta[i] * 0.3, p0, np.ones(b.model.dim), 1e-3, 12, gene_of=[i])
+        th0, pp0, H0 = o.leapfrog_fixed(theta[i] * 0.3, p0, np.ones(b.model.dim), 1e-3, 12)
+        assert _rel(th[0], th0) < 1e-8 and _rel(pp[0], pp0) < 1e-8 and abs(H[0] - H0) < 1e-8 * abs(H0)
+    s = api.Sampler(b, api.nuts_cfg(10, 3, 2, seed=5))
+    want = oracle.Oracle(synth.gene_dict(shared, genes, 0), family).nuts(oracle.nuts_cfg(10, 3, seed=5), gene_id=1,
+                                                                         chain_id=1, save_warmup=True)
+    for it in range(5):
+        s.advance(1)
+        th, eps, _ = s.state()
+        assert np.max(np.abs(th[0, 0] - want["draws"][it, 7:])) < 1e-7, it
+
+
 @pytest.mark.parametrize("order", ["default", "generic"])
 def test_nuts_multi_tile_matches_oracle(order, monkeypatch):
     if order != "default":
