@@ -89,3 +89,56 @@ def test_snap25_real_counts(golden_dir):
     assert (st == 0).all() and (it == 40).all()
     summ = s.spot_summaries()
     assert np.all(np.isfinite(summ["lambda/mean"])) and np.all(summ["lambda/mean"] > 0)
+
+
+def test_cmdstan_argv_shim(golden_dir, tmp_path):
+    """`BINARY sample num_samples=N num_warmup=N random id=CHAIN data file=IN.R output file=OUT.csv refresh=10`
+    (bin/splotch:131): the shim honours the executable's argv so the unmodified reference wrapper can call it."""
+    out = str(tmp_path / "output_3_2.csv")
+    argv = ["/opt/bin/comp_splotch_stan_model", "sample", "num_samples=25", "num_warmup=25", "random", "id=2", "data",
+            "file=" + os.path.join(golden_dir, "c1", "data_3.R"), "output", "file=" + out, "refresh=10"]
+    assert cli.cmdstan_shim(argv) == 0
+    lines = open(out).read().splitlines()
+    assert lines[0].startswith("lp__,") and len(lines) == 26
+    post = stancsv.read_stan_csv(out, ["beta_level_1", "log_lambda", "tau", "a", "theta"])
+    assert post["beta_level_1"].shape == (25, 1, 14, 5) and np.all(post["tau"] > 0) and np.all(post["a"] < 1)
+    assert cli.cmdstan_shim(["/opt/bin/comp_splotch_stan_model", "pathfinder"]) == 1
+
+
+def test_error_behaviour(golden_dir):
+    """Bad inputs are refused with a message, like Stan's data-block validation, never silently."""
+    from csplotch_b200._lib import CsplotchError
+    shared = synth.shared_tiny(seed=1, family="comp_splotch_stan_model")
+    genes = synth.simulate_counts(shared, 2, 2)
+    bad = dict(shared); bad["nb"] = 1
+    with pytest.raises(CsplotchError, match="negative binomial"):
+        api.Model(bad, "comp_splotch_stan_model")
+    bad = dict(shared); bad["D"] = np.asarray(shared["D"]).copy(); bad["D"][0] = 99
+    with pytest.raises(CsplotchError, match="D out of range"):
+        api.Model(bad, "comp_splotch_stan_model")
+    bad = dict(shared); bad["size_factors"] = np.asarray(shared["size_factors"]).copy(); bad["size_factors"][3] = 0.0
+    with pytest.raises(CsplotchError, match="size_factors"):
+        api.Model(bad, "comp_splotch_stan_model")
+    bad = dict(shared); bad["D_sparse"] = np.asarray(shared["D_sparse"]).copy(); bad["D_sparse"][0] += 1
+    with pytest.raises(CsplotchError, match="D_sparse"):
+        api.Model(bad, "comp_splotch_stan_model")
+    big = synth.shared_tiny(seed=1, family="comp_splotch_stan_model", K=17)
+    with pytest.raises(CsplotchError, match="N_celltypes"):
+        api.Model(big, "comp_splotch_stan_model")
+    model = api.Model(shared, "comp_splotch_stan_model")
+    c = genes["counts"].copy(); c[0, 0] = -1
+    with pytest.raises(CsplotchError, match="counts"):
+        api.Batch(model, c, genes["beta_prior_mean"], genes["beta_prior_std"])
+    with pytest.raises(CsplotchError, match="beta_prior"):
+        api.Batch(model, genes["counts"])
+    b = api.Batch(model, genes["counts"], genes["beta_prior_mean"], genes["beta_prior_std"])
+    with pytest.raises(CsplotchError, match="max_depth"):
+        api.Sampler(b, api.nuts_cfg(10, 10, 2, max_depth=20))
+    with pytest.raises(ValueError):
+        api.family_from_binary("/usr/bin/not_a_splotch_model")
+    # an initial point with non-finite density is reported per chain (status 1), other chains run
+    th0 = np.zeros((2, 2, model.dim)); th0[0, 0, :] = 800.0
+    s = api.Sampler(b, api.nuts_cfg(5, 5, 2, seed=1), theta_init=th0)
+    s.run()
+    st, it = s.status()
+    assert st[0, 0] == 1 and it[0, 0] == 0 and (st.reshape(-1)[1:] == 0).all() and (it.reshape(-1)[1:] == 10).all()
