@@ -110,6 +110,7 @@ class Model:
         self.C = int(d["N_covariates"])
         self.levels = (int(d["N_level_1"]), int(d.get("N_level_2", 0)), int(d.get("N_level_3", 0)))
         self.car, self.zi = car, int(d.get("zi", 0))
+        self.nb = int(d.get("nb", 0)) if fam == 1 else 0
         self.level_2_mapping = np.asarray(d.get("level_2_mapping", []), dtype=np.int64).reshape(-1)
         self.level_3_mapping = np.asarray(d.get("level_3_mapping", []), dtype=np.int64).reshape(-1)
 
@@ -146,8 +147,12 @@ class Model:
             cols += ["sigma_level_3.1"]
         if self.zi:
             cols += ["theta.1"]
+        if self.nb:
+            cols += ["phi.1"]
         cols += ["noise_raw.%d" % (i + 1) for i in range(N)]
         cols += ["log_lambda.%d" % (i + 1) for i in range(N)]
+        if self.nb:
+            cols += ["phi_arr.%d" % (i + 1) for i in range(N)]
         for lev, nr in ((1, L1), (2, L2), (3, L3)):
             if comp:
                 cols += ["beta_level_%d.%d.%d.%d" % (lev, i + 1, j + 1, k + 1)
@@ -356,10 +361,12 @@ class Sampler:
             names += ["sigma_level_3"]
         if m.zi:
             names += ["theta"]
+        if m.nb:
+            names += ["phi"]
         out = {}
         for i, nme in enumerate(names):
             u = sc[..., i]
-            out[nme] = (1.0 / (1.0 + np.exp(-u))) if nme in ("a", "theta") else np.exp(u)
+            out[nme] = (1.0 / (1.0 + np.exp(-u))) if nme in ("a", "theta") else np.exp(u) + (1e-6 if nme == "phi" else 0.0)
         if m.family == 1:
             std = self.batch.beta_prior_std[:, None, None, None, :]
             mean = self.batch.beta_prior_mean[:, None, None, None, :]

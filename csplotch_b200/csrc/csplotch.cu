@@ -400,8 +400,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   if (!d || !out) return fail(CSPLOTCH_E_INVALID, "null argument");
   *out = nullptr;
   if (d->family < 0 || d->family > 2) return fail(CSPLOTCH_E_INVALID, "family must be 0,1,2");
-  if (d->family == CSPLOTCH_COMP_SPLOTCH && d->nb)
-    return fail(CSPLOTCH_E_UNSUPPORTED, "nb=1 (negative binomial likelihood) is not built yet");
+  if (d->nb < 0 || d->nb > 2) return fail(CSPLOTCH_E_INVALID, "nb must be 0, 1 (reference semantics) or 2 (per-spot ZINB term)");
   if (d->N_tissues < 1 || !d->N_spots || !d->tissue_mapping || !d->D || !d->size_factors)
     return fail(CSPLOTCH_E_INVALID, "missing N_spots / tissue_mapping / D / size_factors");
   const int T = d->N_tissues, C = d->N_covariates;
@@ -435,6 +434,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   dm.nbeta = L * C * kt;
   dm.nbeta_true = L * C * K;
   dm.zi = zi; dm.car = car;
+  dm.nb = d->family == CSPLOTCH_COMP_SPLOTCH ? d->nb : 0;
   int ns = 0;
   dm.s_tau = car ? ns++ : -1;
   dm.s_a = car ? ns++ : -1;
@@ -442,6 +442,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   dm.s_s2 = L2 ? ns++ : -1;
   dm.s_s3 = L3 ? ns++ : -1;
   dm.s_theta = zi ? ns++ : -1;
+  dm.s_phi = dm.nb ? ns++ : -1;
   dm.nscal = ns;
   dm.nsmall = dm.nbeta + ns;
   dm.nsmall_true = dm.nbeta_true + ns;
@@ -452,7 +453,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   dm.Di = dm.o_small + dm.nsmall_pad;
   dm.D = (car ? N : 0) + dm.nbeta_true + ns + N;
   dm.Nc = dm.Npad;
-  m->n_outputs = dm.D + N + dm.nbeta_true;
+  m->n_outputs = dm.D + N + (dm.nb ? N : 0) + dm.nbeta_true;
 
   // ---- adjacency in original spot ids ---------------------------------------------------------------
   std::vector<std::vector<int>> adj0(car ? N : 0);
@@ -573,6 +574,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     if (cand != m->perm && reach(cand) != 0 && reach(cand) <= reach(m->perm)) m->perm = cand;
   }
   if (force && std::string(force) == "generic") tiled = false;
+  if (dm.nb) tiled = false;  // the NB / ZINB likelihood lives in the generic kernel only
   std::vector<int> inv(N);
   for (int j = 0; j < N; ++j) inv[m->perm[j]] = j;
   int ell_w = 0;
@@ -1176,6 +1178,7 @@ k_write_array(const __grid_constant__ DevModel m_in, const double *__restrict__ 
         else if (sidx == m.s_s2) v = sc.s2;
         else if (sidx == m.s_s3) v = sc.s3;
         else if (sidx == m.s_theta) v = sc.theta;
+        else if (sidx == m.s_phi) v = sc.phi;
       }
       // beta_raw is written column-major over (i,j,k): first index fastest
       int oi = si;
@@ -1201,7 +1204,9 @@ k_write_array(const __grid_constant__ DevModel m_in, const double *__restrict__ 
       ll += sig03 * q[m.o_noise + j];
       oll[perm[j]] = ll;
     }
-    double *ob = oll + m.N;
+    if (m.nb)
+      for (int j = threadIdx.x; j < m.N; j += kBlock) oll[m.N + j] = sc.phi;  // transformed parameter phi_arr
+    double *ob = oll + m.N + (m.nb ? m.N : 0);
     for (int idx = threadIdx.x; idx < m.nbeta; idx += kBlock) {
       const int i = idx / CK, rem = idx - i * CK, j = rem / m.K, k = rem - j * m.K;
       if (k >= m.Ktrue) continue;

@@ -32,10 +32,11 @@ struct DevModel {
   int family, N, Npad, C, K, L1, L2, L3, L, bot0, nbeta, nscal, nsmall, nsmall_pad;
   int Ktrue, nbeta_true, nsmall_true;  // K is the padded (template) cell-type count; *_true are Stan's
   int zi, car;
+  int nb;  // comp only: 0 Poisson/ZIP, 1 NB/ZINB exactly as the reference writes it (ZINB term x N), 2 per-spot ZINB term
   int D;   // Stan dimension
   int Di;  // internal dimension (padded)
   int o_psi, o_noise, o_small;
-  int s_tau, s_a, s_sigma, s_s2, s_s3, s_theta;  // index inside the scalar part, -1 if absent
+  int s_tau, s_a, s_sigma, s_s2, s_s3, s_theta, s_phi;  // index inside the scalar part, -1 if absent
   int n_eig;
   int Nc;      // row stride of the counts matrix (int32 elements) = Npad
   int NT;      // tiles of kTile spots; Npad = NT * kTile
@@ -73,7 +74,18 @@ struct Scalars {
   double jac;          // sum of log-Jacobians
   double log_tau;      // = the unconstrained value itself
   double log1m_theta;  // log(1 - theta), shared with the log-Jacobian of theta
+  double log_theta;
+  double phi, log_phi; // NB overdispersion (comp_splotch_stan_model.stan:104), 0 unless nb
 };
+
+// digamma by upward recurrence to x >= 10 and the asymptotic series (abs. error < 1e-15)
+__device__ __forceinline__ double digamma_d(double x) {
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return r + log(x) - 0.5 / x + t;
+}
 
 // x = inv_logit(u) together with log x and log(1 - x) from ONE exp and ONE log1p
 // (log_inv_logit(u) = min(u,0) - log1p(e^{-|u|}), log1m_inv_logit(u) = min(-u,0) - log1p(e^{-|u|}))
@@ -254,6 +266,7 @@ struct DevOps {
     const double u_tau = ss[max(0, min(m.s_tau, last))], u_a = ss[max(0, min(m.s_a, last))];
     const double u_sigma = ss[m.s_sigma], u_s2 = ss[max(0, min(m.s_s2, last))];
     const double u_s3 = ss[max(0, min(m.s_s3, last))], u_theta = ss[max(0, min(m.s_theta, last))];
+    const double u_phi = ss[max(0, min(m.s_phi, last))];
     sc.log_tau = 0.0;
     sc.log1m_theta = 0.0;
     if (m.car) {
@@ -268,10 +281,16 @@ struct DevOps {
     jac += u_sigma;
     if (m.L2) { sc.s2 = exp(u_s2); jac += u_s2; }
     if (m.L3) { sc.s3 = exp(u_s3); jac += u_s3; }
+    sc.log_theta = 0.0;
     if (m.zi) {
-      double lt;
-      logit_triple(u_theta, sc.theta, lt, sc.log1m_theta);
-      jac += lt + sc.log1m_theta;
+      logit_triple(u_theta, sc.theta, sc.log_theta, sc.log1m_theta);
+      jac += sc.log_theta + sc.log1m_theta;
+    }
+    sc.phi = sc.log_phi = 0.0;
+    if (m.nb) {
+      sc.phi = 1e-6 + exp(u_phi);
+      sc.log_phi = log(sc.phi);
+      jac += u_phi;
     }
     sc.jac = jacobian ? jac : 0.0;
     const int CK = m.C * m.K;
@@ -322,15 +341,15 @@ struct DevOps {
                          double a_kin, double a_g2, double tails, double *dq, double *dg, double *dp, double eps,
                          double *V_out, double *K_out, bool *finite_out, const double *sp = nullptr,
                          double *rho_out = nullptr, double a_pp = 0.0, double *pp_out = nullptr,
-                         bool eig_done = false, double a_ldet = 0.0, double a_dldet = 0.0) {
+                         bool eig_done = false, double a_ldet = 0.0, double a_dldet = 0.0, double a_dphi = 0.0) {
     const int tid = threadIdx.x;
     // momenta / metric entries of the (<= 6) scalars: one batch of independent loads issued now, so that
     // their latency overlaps the reductions below instead of stalling the scalar epilogue
     const int so = m.o_small + m.nbeta;
-    const int sidx[6] = {m.s_tau, m.s_a, m.s_sigma, m.s_s2, m.s_s3, m.s_theta};
-    double ph_s[6], mi_s[6], po_s[6];
+    const int sidx[7] = {m.s_tau, m.s_a, m.s_sigma, m.s_s2, m.s_s3, m.s_theta, m.s_phi};
+    double ph_s[7], mi_s[7], po_s[7];
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
+    for (int s = 0; s < 7; ++s) {
       const int e = so + max(0, sidx[s]);
       ph_s[s] = LEAP ? dp[e] : 0.0;
       mi_s[s] = LEAP ? minv[e] : 0.0;
@@ -350,8 +369,8 @@ struct DevOps {
     const double *sb = dq + m.o_small;
     for (int idx = tid; idx < m.nbeta; idx += kBlock) a_lp -= 0.5 * sb[idx] * sb[idx];
 
-    double r1[9] = {a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_ldet, a_dldet, a_g2};
-    block_sum<9>(r1, red);  // also orders the shared atomics on adjB before the reads below
+    double r1[10] = {a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_ldet, a_dldet, a_g2, a_dphi};
+    block_sum<10>(r1, red);  // also orders the shared atomics on adjB before the reads below
 
     // reverse of the hierarchy (A.3): parents collect their children
     const int CK = m.C * m.K;
@@ -404,7 +423,7 @@ struct DevOps {
     double lp = r1[0] + sc.jac;
     double kin = r1[5] + r2[2];
     double g2 = r1[8] + r2[3];
-    double gu_tau = 0, gu_a = 0, gu_sigma, gu_s2 = 0, gu_s3 = 0, gu_theta = 0;
+    double gu_tau = 0, gu_a = 0, gu_sigma, gu_s2 = 0, gu_s3 = 0, gu_theta = 0, gu_phi = 0;
     if (m.car) {
       const double Q = r1[2] - sc.a * r1[3];
       const double inv_tau = 1.0 / sc.tau;
@@ -421,16 +440,20 @@ struct DevOps {
     if (m.L3) { lp += -0.5 * sc.s3 * sc.s3; gu_s3 = sc.s3 * (-sc.s3 + r2[1]) + (jacobian ? 1.0 : 0.0); }
     if (m.zi) {
       lp += tails;                      // theta ~ beta(1,2)
-      lp += gn.nnz * tails - gn.lgam;   // bernoulli(0|theta) and -lgamma(y+1) of the non-zero spots
+      lp += gn.nnz * tails - (m.nb ? 0.0 : gn.lgam);  // bernoulli(0|theta) and -lgamma(y+1) of the non-zero spots
       const double d_theta = r1[4] - (gn.nnz + 1.0) / (1.0 - sc.theta);
       gu_theta = sc.theta * (1.0 - sc.theta) * d_theta + (jacobian ? (1.0 - 2.0 * sc.theta) : 0.0);
     }
+    if (m.nb) {
+      lp += sc.log_phi - sc.phi;  // phi ~ gamma(2,1)
+      gu_phi = (sc.phi - 1e-6) * (r1[9] + 1.0 / sc.phi - 1.0) + (jacobian ? 1.0 : 0.0);
+    }
     // read phase (all threads) then write phase (thread 0) of the scalar momenta
-    double pn_s[6] = {0, 0, 0, 0, 0, 0};
+    double pn_s[7] = {0, 0, 0, 0, 0, 0, 0};
     double pp = r2[4];
-    const double gu[6] = {gu_tau, gu_a, gu_sigma, gu_s2, gu_s3, gu_theta};
+    const double gu[7] = {gu_tau, gu_a, gu_sigma, gu_s2, gu_s3, gu_theta, gu_phi};
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
+    for (int s = 0; s < 7; ++s) {
       if (sidx[s] >= 0) {
         g2 += gu[s] * gu[s];
         if (LEAP) {
@@ -443,7 +466,7 @@ struct DevOps {
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-      for (int s = 0; s < 6; ++s) {
+      for (int s = 0; s < 7; ++s) {
         if (sidx[s] >= 0) {
           dg[so + sidx[s]] = -gu[s];
           if (LEAP) dp[so + sidx[s]] = pn_s[s];
@@ -886,9 +909,12 @@ struct DevOps {
     for (int idx = tid; idx < m.nbeta; idx += kBlock) adjB[idx] = 0.0;
     __syncthreads();
 
-    const double heads = m.zi ? log(sc.theta) : 0.0;
-    const double tails = m.zi ? log1p(-sc.theta) : 0.0;
+    const double heads = sc.log_theta;
+    const double tails = sc.log1m_theta;
     const double sig03 = 0.3 * sc.sigma;
+    const double nb_mult = (m.nb == 1 && m.zi) ? (double)m.N : 1.0;
+    const double lgam_phi = m.nb ? lgamma(sc.phi) : 0.0, dig_phi = m.nb ? digamma_d(sc.phi) : 0.0;
+    double a_dphi = 0.0;
     const double *psi = dq + m.o_psi;
     const double *noi = dq + m.o_noise;
     double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0, a_pp = 0;
@@ -935,7 +961,34 @@ struct DevOps {
         const double eta = ll + m.lsf[j];
         const double mu = exp(eta);
         const int y = gn.counts[j];
-        if (m.zi && y == 0) {
+        if (m.nb) {
+          // neg_binomial_2_log (comp_splotch_stan_model.stan:248-265); mult = N reproduces the phi_arr
+          // broadcast of the ZINB branch as the reference writes it (nb == 1), 1 the per-spot term (nb == 2)
+          const double yd = (double)y;
+          const double dl = eta - sc.log_phi;
+          const double L = dl > 0 ? dl + log1p(exp(-dl)) : log1p(exp(dl));
+          const double sg = inv_logit_d(dl);
+          const double nbv = lgamma(yd + sc.phi) - lgamma(yd + 1.0) - lgam_phi + yd * eta - sc.phi * L - yd * (sc.log_phi + L);
+          const double dnb_deta = yd - (sc.phi + yd) * sg;
+          const double dnb_dphi = digamma_d(yd + sc.phi) - dig_phi - L + (sc.phi + yd) * sg / sc.phi - yd / sc.phi;
+          if (m.zi && y == 0) {
+            const double Bq = tails + nb_mult * nbv;
+            const double dd = heads - Bq;
+            const double t = exp(-fabs(dd));
+            const double l1p = log1p(t);
+            const double wmax = 1.0 / (1.0 + t), wmin = t / (1.0 + t);
+            const double wA = dd >= 0 ? wmax : wmin;
+            const double wB = dd >= 0 ? wmin : wmax;
+            a_lp += (dd >= 0 ? heads : Bq) + l1p;
+            gj = wB * nb_mult * dnb_deta;
+            a_dphi += wB * nb_mult * dnb_dphi;
+            a_dth += wA / sc.theta - wB / (1.0 - sc.theta);
+          } else {
+            a_lp += nb_mult * nbv;   // (zi: log1m theta of the non-zero spots is added once in finish())
+            gj = nb_mult * dnb_deta;
+            a_dphi += nb_mult * dnb_dphi;
+          }
+        } else if (m.zi && y == 0) {
           // log_sum_exp(log theta, log1m theta - mu) and its softmax weights
           const double Bq = tails - mu;
           const double dd = heads - Bq;
@@ -1008,7 +1061,7 @@ struct DevOps {
     }
 
     finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out, sp, rho_out,
-                 a_pp, pp_out);
+                 a_pp, pp_out, false, 0.0, 0.0, a_dphi);
   }
 
   // ---- Ops interface of nuts_core.h ---------------------------------------------------------------

@@ -38,7 +38,7 @@ extern "C" {
 enum {
   CSPLOTCH_OK = 0,
   CSPLOTCH_E_INVALID = 1,     /* bad argument / inconsistent data block */
-  CSPLOTCH_E_UNSUPPORTED = 2, /* e.g. nb=1 (NB/ZINB branch not built yet) */
+  CSPLOTCH_E_UNSUPPORTED = 2, /* e.g. N_celltypes > 16 */
   CSPLOTCH_E_CUDA = 3,        /* CUDA runtime error; message has the cause */
   CSPLOTCH_E_NOMEM = 4
 };
@@ -63,7 +63,10 @@ typedef struct {
   int32_t N_covariates;
   int32_t N_celltypes;             /* comp only, else 1 */
   int32_t N_level_1, N_level_2, N_level_3;
-  int32_t zi, car, nb;
+  int32_t zi, car;
+  int32_t nb;                      /* comp only: 0 Poisson/ZIP; 1 NB/ZINB exactly as comp_...stan:248-265 evaluates it (the
+                                      ZINB branch passes the vector phi_arr to a scalar-count lpmf, so every spot's NB
+                                      term counts N times); 2 = ZINB with the per-spot term counted once */
   const int32_t *level_2_mapping;  /* [N_level_2], 1-based */
   const int32_t *level_3_mapping;  /* [N_level_3], 1-based */
   const int32_t *tissue_mapping;   /* [N_tissues], 1-based */

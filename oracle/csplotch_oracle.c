@@ -36,6 +36,14 @@ static double inv_logit(double u) {
   }
   return 1.0 / (1.0 + exp(-u));
 }
+/* digamma by upward recurrence to x >= 10 and the asymptotic series (abs. error < 1e-15) */
+static double digamma_(double x) {
+  double r = 0.0, f, t;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  f = 1.0 / (x * x);
+  t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return r + log(x) - 0.5 / x + t;
+}
 static double log_inv_logit(double u) { return u < 0 ? u - log1p(exp(u)) : -log1p(exp(-u)); }
 static double log1m_inv_logit(double u) { return u > 0 ? -u - log1p(exp(-u)) : -log1p(exp(u)); }
 
@@ -91,8 +99,8 @@ int32_t orc_num_spots(const orc_data *d) { lay_t l; layout(d, &l); return l.N; }
 int32_t orc_dim(const orc_data *d) { lay_t l; layout(d, &l); return l.D; }
 int32_t orc_num_outputs(const orc_data *d) {
   lay_t l; layout(d, &l);
-  /* params (constrained, same count as D) + log_lambda + beta_level_1..3 */
-  return l.D + l.N + l.nbeta;
+  /* params (constrained, same count as D) + log_lambda + [phi_arr] + beta_level_1..3 */
+  return l.D + l.N + (l.nb ? l.N : 0) + l.nbeta;
 }
 
 /* transformed parameters{}: beta_level_k, stacked as rows [0,L) of b[(i*C+j)*K+k].
@@ -178,15 +186,14 @@ double orc_log_prob_grad(const orc_data *d, const double *th, double *grad, int3
   lay_t l;
   int i, j, k, N;
   double lp = 0.0;
-  double tau = 0, a = 0, sigma, s2 = 0, s3 = 0, theta = 0;
-  double d_tau = 0, d_a = 0, d_sigma = 0, d_s2 = 0, d_s3 = 0, d_theta = 0;
+  double tau = 0, a = 0, sigma, s2 = 0, s3 = 0, theta = 0, phi = 0;
+  double d_tau = 0, d_a = 0, d_sigma = 0, d_s2 = 0, d_s3 = 0, d_theta = 0, d_phi = 0;
   const double *psi, *braw, *noise;
   double *b, *adj_b, *ll, *adj_ll, *Wpsi = NULL;
   int *row_of_spot;
 
   layout(d, &l);
   N = l.N;
-  if (l.nb) return NAN; /* NB/ZINB branch (comp_…stan:248-265) is SURVEY §8 f3 "next" */
   psi = th + l.o_psi;
   braw = th + l.o_beta;
   noise = th + l.o_noise;
@@ -208,6 +215,11 @@ double orc_log_prob_grad(const orc_data *d, const double *th, double *grad, int3
     double u = th[l.o_theta];
     theta = inv_logit(u);
     if (jacobian) lp += log_inv_logit(u) + log1m_inv_logit(u);
+  }
+
+  if (l.nb) { /* real<lower=0.000001> phi[nb ? 1 : 0]  (comp_splotch_stan_model.stan:104) */
+    phi = 1e-6 + exp(th[l.o_phi]);
+    if (jacobian) lp += th[l.o_phi];
   }
 
   /* ---- transformed parameters{} ---- */
@@ -261,7 +273,47 @@ double orc_log_prob_grad(const orc_data *d, const double *th, double *grad, int3
   }
 
   /* likelihood */
-  if (l.zi) {
+  if (l.nb) {
+    /* comp_splotch_stan_model.stan:248-265.  neg_binomial_2_log_lpmf(n | eta, phi) =
+     * binomial_coefficient_log(n + phi - 1, n) + n eta - phi log1p_exp(eta - log phi) - n log_sum_exp(eta, log phi).
+     * QUIRK (nb == 1, the reference as written): in the ZINB branch the scalar-count lpmf is called with the
+     * VECTOR phi_arr (:257,:260), so Stan broadcasts and returns the sum over N identical terms = N x the
+     * per-spot term.  nb == 2 evaluates the per-spot term once (the evident intent). */
+    const double mult = (l.zi && d->nb == 1) ? (double)N : 1.0;
+    const double logphi = log(phi);
+    const double heads = l.zi ? log(theta) : 0.0, tails = l.zi ? log1m(theta) : 0.0;
+    lp += (2.0 - 1.0) * logphi - 1.0 * phi; /* phi ~ gamma(2,1) */
+    d_phi += 1.0 / phi - 1.0;
+    for (j = 0; j < N; ++j) {
+      int y = d->counts[j];
+      double eta = ll[j] + log(d->size_factors[j]);
+      double L = log1p_exp(eta - logphi);
+      double sg = inv_logit(eta - logphi);
+      double nbv = lgamma(y + phi) - lgamma(y + 1.0) - lgamma(phi) + y * eta - phi * L - y * (logphi + L);
+      double dnb_deta = y - (phi + y) * sg;
+      double dnb_dphi = digamma_(y + phi) - digamma_(phi) - L + (phi + y) * sg / phi - y / phi;
+      if (l.zi) {
+        if (y == 0) {
+          double B = tails + mult * nbv;
+          double lse = log_sum_exp2(heads, B);
+          double wA = exp(heads - lse), wB = exp(B - lse);
+          lp += lse;
+          adj_ll[j] += wB * mult * dnb_deta;
+          d_phi += wB * mult * dnb_dphi;
+          d_theta += wA / theta - wB / (1.0 - theta);
+        } else {
+          lp += tails + mult * nbv;
+          adj_ll[j] += mult * dnb_deta;
+          d_phi += mult * dnb_dphi;
+          d_theta += -1.0 / (1.0 - theta);
+        }
+      } else {
+        lp += nbv;
+        adj_ll[j] += dnb_deta;
+        d_phi += dnb_dphi;
+      }
+    }
+  } else if (l.zi) {
     double heads = log(theta), tails = log1m(theta);
     if (l.fam == 2) {
       /* zero / non-zero split: splotch_stan_model_csr.stan:254-268 */
@@ -383,6 +435,7 @@ double orc_log_prob_grad(const orc_data *d, const double *th, double *grad, int3
     if (l.L2) grad[l.o_s2] = s2 * d_s2 + (jacobian ? 1.0 : 0.0);
     if (l.L3) grad[l.o_s3] = s3 * d_s3 + (jacobian ? 1.0 : 0.0);
     if (l.zi) grad[l.o_theta] = theta * (1.0 - theta) * d_theta + (jacobian ? (1.0 - 2.0 * theta) : 0.0);
+    if (l.nb) grad[l.o_phi] = (phi - 1e-6) * d_phi + (jacobian ? 1.0 : 0.0);
   }
 
   free(b); free(adj_b); free(ll); free(adj_ll); free(row_of_spot);
@@ -419,6 +472,7 @@ void orc_write_array(const orc_data *d, const double *th, double *out) {
   beta_levels(d, &l, th + l.o_beta, s2, s3, b);
   compute_log_lambda(d, &l, b, th + l.o_psi, sigma, th + l.o_noise, ll, NULL);
   for (i = 0; i < l.N; ++i) out[o++] = ll[i];
+  if (l.nb) for (i = 0; i < l.N; ++i) out[o++] = 1e-6 + exp(th[l.o_phi]); /* phi_arr */
   for (lev = 0; lev < 3; ++lev) {
     int r0 = lev == 0 ? 0 : (lev == 1 ? l.L1 : l.L1 + l.L2);
     int nr = lev == 0 ? l.L1 : (lev == 1 ? l.L2 : l.L3);

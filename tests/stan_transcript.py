@@ -54,6 +54,10 @@ def stan_log_prob(d, family, theta, jacobian=True):
     if zi:
         u = take(1)[0]; theta_zi = torch.sigmoid(u)
         if jacobian: lp = lp + torch.log(theta_zi) + torch.log1p(-theta_zi)
+    nb = int(d.get("nb", 0)) if comp else 0
+    if nb:
+        u = take(1)[0]; phi = 1e-6 + torch.exp(u)
+        if jacobian: lp = lp + u
     noise_raw = take(N)
     assert pos == theta.numel()
 
@@ -109,7 +113,21 @@ def stan_log_prob(d, family, theta, jacobian=True):
 
     y = torch.tensor(np.asarray(d["counts"], dtype=np.float64))
     eta = log_lambda + torch.log(torch.tensor(np.asarray(d["size_factors"], dtype=np.float64)))
-    if zi:
+    if nb:
+        lp = lp + torch.log(phi) - phi                               # gamma(2,1), constants dropped
+        # neg_binomial_2_log_lpmf as Stan writes it (binomial_coefficient_log kept whole)
+        logphi = torch.log(phi)
+        L = torch.nn.functional.softplus(eta - logphi)
+        nbv = torch.lgamma(y + phi) - torch.lgamma(y + 1.0) - torch.lgamma(phi) + y * eta - phi * L - y * (logphi + L)
+        if zi:
+            mult = float(N) if nb == 1 else 1.0                     # phi_arr broadcast of the reference (comp_...stan:257,260)
+            heads = torch.log(theta_zi); tails = torch.log1p(-theta_zi)
+            zero = y == 0
+            lp = lp + torch.logsumexp(torch.stack([heads.expand(int(zero.sum())), tails + mult * nbv[zero]]), 0).sum()
+            lp = lp + (tails + mult * nbv[~zero]).sum()
+        else:
+            lp = lp + nbv.sum()
+    elif zi:
         heads = torch.log(theta_zi); tails = torch.log1p(-theta_zi)
         zero = y == 0
         lp = lp + torch.logsumexp(torch.stack([heads.expand(int(zero.sum())), tails - torch.exp(eta[zero])]), 0).sum()

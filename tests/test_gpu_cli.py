@@ -110,8 +110,8 @@ def test_error_behaviour(golden_dir):
     from csplotch_b200._lib import CsplotchError
     shared = synth.shared_tiny(seed=1, family="comp_splotch_stan_model")
     genes = synth.simulate_counts(shared, 2, 2)
-    bad = dict(shared); bad["nb"] = 1
-    with pytest.raises(CsplotchError, match="negative binomial"):
+    bad = dict(shared); bad["nb"] = 7
+    with pytest.raises(CsplotchError, match="nb must be"):
         api.Model(bad, "comp_splotch_stan_model")
     bad = dict(shared); bad["D"] = np.asarray(shared["D"]).copy(); bad["D"][0] = 99
     with pytest.raises(CsplotchError, match="D out of range"):

@@ -154,6 +154,39 @@ def test_lp_grad_all_kernel_paths(family, order, monkeypatch):
         assert np.allclose(b.write_array(theta[i:i + 1], gene_of=[i])[0], oi.write_array(theta[i]), rtol=1e-13, atol=1e-13)
 
 
+@pytest.mark.parametrize("zi,nb", [(0, 1), (1, 1), (1, 2)])
+def test_negative_binomial_likelihood(zi, nb):
+    """NB / ZINB branch of comp_splotch_stan_model.stan:248-265 (nb=1: the ZINB term x N exactly as the
+    reference's phi_arr broadcast evaluates it; nb=2: per-spot term)."""
+    family = "comp_splotch_stan_model"
+    shared, genes = _tiny(family, 2, zi, 1, seed=60 + zi, G=2)
+    shared = dict(shared); shared["nb"] = nb
+    b = _batch(shared, genes, family, gene_id0=4)
+    rng = np.random.default_rng(5)
+    theta = rng.normal(0, 1.0, (4, b.model.dim))
+    gene_of = np.array([0, 1, 0, 1])
+    lp, grad = b.log_prob_grad(theta, gene_of=gene_of)
+    cols = b.model.column_names()
+    assert "phi.1" in cols and cols.index("phi_arr.1") == cols.index("log_lambda.1") + b.model.N
+    for i in range(4):
+        o = oracle.Oracle(synth.gene_dict(shared, genes, int(gene_of[i])), family)
+        lp0, g0 = o.log_prob_grad(theta[i])
+        assert abs(lp[i] - lp0) <= 1e-10 * max(1.0, abs(lp0)), (i, lp[i], lp0)
+        assert _rel(grad[i], g0) < 1e-10
+        assert np.allclose(b.write_array(theta[i:i + 1], gene_of=[int(gene_of[i])])[0], o.write_array(theta[i]),
+                           rtol=1e-12, atol=1e-12)
+    s = api.Sampler(b, api.nuts_cfg(15, 5, 2, seed=3))
+    want = oracle.Oracle(synth.gene_dict(shared, genes, 0), family).nuts(oracle.nuts_cfg(15, 5, seed=3), gene_id=4,
+                                                                         chain_id=1, save_warmup=True)
+    for it in range(6):
+        s.advance(1)
+        th, eps, _ = s.state()
+        assert np.max(np.abs(th[0, 0] - want["draws"][it, 7:])) < 1e-7, it
+    s.advance(20)
+    ex = s.extract_small()
+    assert ex["phi"].shape == (2, 10) and np.all(ex["phi"] > 1e-6)
+
+
 def test_wide_rows_need_two_tile_reach():
     """Visium-HD style: 300-wide row-major grids put the vertical neighbour 300 spots (two 256-spot tiles)
     away; the tiled pipeline then drifts psi two tiles ahead (LOOK = 2, non-compositional kernels)."""

@@ -148,3 +148,27 @@ def test_oracle_vs_mpmath_50_digits():
             lp += mp.log(1 - thz) + y * eta - mp.e ** eta - mp.loggamma(y + 1)
     got = o.log_prob_grad(th, want_grad=False)
     assert abs(got - float(lp)) < 1e-12 * abs(float(lp))
+
+
+@pytest.mark.parametrize("zi,nb", [(0, 1), (1, 1), (1, 2)])
+def test_negative_binomial_branch(zi, nb):
+    """NB / ZINB likelihood of comp_splotch_stan_model.stan:248-265 incl. the phi_arr broadcast of the ZINB
+    branch as written (nb=1) and the per-spot variant (nb=2)."""
+    shared, genes = _case("comp_splotch_stan_model", 2, zi, 1, seed=31 + zi)
+    shared = dict(shared); shared["nb"] = nb
+    d = synth.gene_dict(shared, genes, 0)
+    o = oracle.Oracle(d, "comp_splotch_stan_model")
+    N = int(np.sum(d["N_spots"]))
+    assert o.dim == 2 * N + o.dim - 2 * N and o.n_out == o.dim + 2 * N + (o.dim - 2 * N - (4 + zi + 1))
+    rng = np.random.default_rng(3)
+    for scale in (0.5, 1.5):
+        th = rng.normal(0, scale, o.dim)
+        for jac in (True, False):
+            lp, g = o.log_prob_grad(th, jacobian=jac)
+            lp2, g2 = stan_log_prob_grad(d, "comp_splotch_stan_model", th, jacobian=jac)
+            assert abs(lp - lp2) <= 1e-11 * max(1.0, abs(lp2))
+            assert np.max(np.abs(g - g2) / np.maximum(1.0, np.abs(g2))) < 1e-10
+    wa = o.write_array(th)
+    assert np.allclose(o.unconstrain(wa[:o.dim]), th, rtol=1e-12, atol=1e-12)
+    phi = 1e-6 + np.exp(th[N + (o.dim - 2 * N - (4 + zi + 1)) + 4 + zi])
+    assert np.allclose(wa[o.dim + N:o.dim + 2 * N], phi)           # phi_arr follows log_lambda
