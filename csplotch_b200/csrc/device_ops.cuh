@@ -1112,14 +1112,12 @@ struct DevOps {
     const double *Cpb = vec(C.pb), *Cpe = vec(C.pe), *Crho = vec(C.rho);
     double *out = vec(rho_out);
     double a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0;
-    for (int e = 2 * threadIdx.x; e < m.Di; e += 2 * kBlock) {
-      const double2 w = *reinterpret_cast<const double2 *>(minv + e);
-      const double2 lpb = *reinterpret_cast<const double2 *>(Lpb + e);
-      const double2 lpe = *reinterpret_cast<const double2 *>(Lpe + e);
-      const double2 lrh = *reinterpret_cast<const double2 *>(Lrho + e);
-      const double2 cpb = *reinterpret_cast<const double2 *>(Cpb + e);
-      const double2 cpe = *reinterpret_cast<const double2 *>(Cpe + e);
-      const double2 crh = *reinterpret_cast<const double2 *>(Crho + e);
+    const int Di = m.Di;
+    const double *mv = minv;
+    // streaming pass over 7 vectors: two strips of 16 B per thread in flight (14 independent loads) keep a
+    // lone merging CTA from being latency bound while its neighbours on the SM do arithmetic
+    auto body = [&](const double2 w, const double2 lpb, const double2 lpe, const double2 lrh, const double2 cpb,
+                    const double2 cpe, const double2 crh, double *o) {
       double2 rs;
       rs.x = lrh.x + crh.x;
       rs.y = lrh.y + crh.y;
@@ -1131,15 +1129,41 @@ struct DevOps {
       const double rcx = crh.x + lpe.x, rcy = crh.y + lpe.y;
       c1 += (w.x * lpe.x) * rcx + (w.y * lpe.y) * rcy;
       c2 += (w.x * cpe.x) * rcx + (w.y * cpe.y) * rcy;
-      *reinterpret_cast<double2 *>(out + e) = rs;
+      *reinterpret_cast<double2 *>(o) = rs;
+    };
+#define CSP_LD2(p, e) (*reinterpret_cast<const double2 *>((p) + (e)))
+    int e = 2 * threadIdx.x;
+    for (; e + 2 * kBlock < Di; e += 4 * kBlock) {
+      const int f = e + 2 * kBlock;
+      const double2 w0 = CSP_LD2(mv, e), w1 = CSP_LD2(mv, f);
+      const double2 p0 = CSP_LD2(Lpb, e), p1 = CSP_LD2(Lpb, f);
+      const double2 q0 = CSP_LD2(Lpe, e), q1 = CSP_LD2(Lpe, f);
+      const double2 r0 = CSP_LD2(Lrho, e), r1 = CSP_LD2(Lrho, f);
+      const double2 s0 = CSP_LD2(Cpb, e), s1 = CSP_LD2(Cpb, f);
+      const double2 t0 = CSP_LD2(Cpe, e), t1 = CSP_LD2(Cpe, f);
+      const double2 u0 = CSP_LD2(Crho, e), u1 = CSP_LD2(Crho, f);
+      body(w0, p0, q0, r0, s0, t0, u0, out + e);
+      body(w1, p1, q1, r1, s1, t1, u1, out + f);
     }
+    for (; e < Di; e += 2 * kBlock)
+      body(CSP_LD2(mv, e), CSP_LD2(Lpb, e), CSP_LD2(Lpe, e), CSP_LD2(Lrho, e), CSP_LD2(Cpb, e), CSP_LD2(Cpe, e),
+           CSP_LD2(Crho, e), out + e);
     double r[6] = {a1, a2, b1, b2, c1, c2};
     block_sum<6>(r, red);
     return (r[1] > 0 && r[0] > 0) && (r[3] > 0 && r[2] > 0) && (r[5] > 0 && r[4] > 0);
   }
   __device__ __noinline__ void copy_vec(double *dst, const double *src) {
-    for (int e = 2 * threadIdx.x; e < m.Di; e += 2 * kBlock)
-      *reinterpret_cast<double2 *>(dst + e) = *reinterpret_cast<const double2 *>(src + e);
+    const int Di = m.Di;
+    int e = 2 * threadIdx.x;
+    for (; e + 6 * kBlock < Di; e += 8 * kBlock) {  // four 16-byte loads in flight per thread
+      const double2 a = CSP_LD2(src, e), b = CSP_LD2(src, e + 2 * kBlock), c = CSP_LD2(src, e + 4 * kBlock),
+                    d = CSP_LD2(src, e + 6 * kBlock);
+      *reinterpret_cast<double2 *>(dst + e) = a;
+      *reinterpret_cast<double2 *>(dst + e + 2 * kBlock) = b;
+      *reinterpret_cast<double2 *>(dst + e + 4 * kBlock) = c;
+      *reinterpret_cast<double2 *>(dst + e + 6 * kBlock) = d;
+    }
+    for (; e < Di; e += 2 * kBlock) *reinterpret_cast<double2 *>(dst + e) = CSP_LD2(src, e);
     __syncthreads();
   }
   __device__ void copy_q_to_prop(int z) {
