@@ -158,12 +158,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~the hint
+  // elapses) instead of burning issue slots of the other CTA on the SM in a polling loop
   uint32_t ok;
   do {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
   } while (!ok);
 }
@@ -765,9 +767,19 @@ struct DevOps {
           // ELL entries are ring positions (neighbour id & (4T-1)); missing neighbours point at the
           // always-zero cell ring[4T], so the gather is branch-free
           const unsigned short *el = reinterpret_cast<const unsigned short *>(ri + 2 * kTile) + tid;
+          // (the widths that occur: 4 = ST / HD grids, 6 = Visium hex; anything else takes the 8-wide form)
           unsigned short pos[kMaxEll];
+          const int ew = c.ell_w;
+          if (ew == 6) {
 #pragma unroll
-          for (int w = 0; w < kMaxEll; ++w) pos[w] = (w < c.ell_w) ? el[w * kTile] : (unsigned short)(RMASK + 1);
+            for (int w = 0; w < 6; ++w) pos[w] = el[w * kTile];
+          } else if (ew == 4) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) pos[w] = el[w * kTile];
+          } else {
+#pragma unroll
+            for (int w = 0; w < kMaxEll; ++w) pos[w] = (w < ew) ? el[w * kTile] : (unsigned short)(RMASK + 1);
+          }
           // split barrier: every thread announced its part of ring(k+1) right after drifting it; only now,
           // with the independent work above already issued, do we need all of them
           if (k + LOOK < NT) {
@@ -775,9 +787,14 @@ struct DevOps {
             mbar_wait(c.mbar + 6 + (sl & 1u), (sl >> 1) & 1u);
           }
           psi_j = ringp[j & RMASK];
+          if (ew == 6) {
+            Wpsi = ((ringp[pos[0]] + ringp[pos[1]]) + (ringp[pos[2]] + ringp[pos[3]])) + (ringp[pos[4]] + ringp[pos[5]]);
+          } else if (ew == 4) {
+            Wpsi = (ringp[pos[0]] + ringp[pos[1]]) + (ringp[pos[2]] + ringp[pos[3]]);
+          } else {
 #pragma unroll
-          for (int w = 0; w < kMaxEll; ++w)
-            if (w < c.ell_w) Wpsi += ringp[pos[w]];
+            for (int w = 0; w < kMaxEll; ++w) Wpsi += ringp[pos[w]];
+          }
           ll += psi_j;
         }
         ll += sig03 * eps_j;

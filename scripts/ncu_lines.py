@@ -49,3 +49,8 @@ for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
     st = sorted(((v, k) for k, v in a.items() if k.startswith("stall_")), reverse=True)[:3]
     print("%5.1f%% smp %5.1f%% ins  %s:%d  %s   [%s]" % (100 * a["samples"] / max(tot, 1), 100 * a["inst"] / max(toti, 1),
           key[0], key[1], src[key].strip()[:70], ", ".join("%s %d" % (k[6:], v) for v, k in st)))
+
+print("---- by instruction share ----")
+for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["inst"])[:top]:
+    print("%5.1f%% ins %5.1f%% smp  %s:%d  %s" % (100 * a["inst"] / max(toti, 1), 100 * a["samples"] / max(tot, 1), key[0], key[1],
+          src[key].strip()[:90]))
