@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-genes", type=int, default=0)
+    ap.add_argument("--e2e-iters", type=int, default=0, help="NUTS transitions per chain in one e2e step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 3) if os.environ.get("CSPLOTCH_BENCH_STRICT", "1") == "1" else args.warmup
@@ -254,31 +255,41 @@ def main():
     del sampler
 
     # ---- e2e arm: host buffers through the C ABI, copies inside the timed region --------------------
+    # One step = one complete small job for a gene block through the public API, the way bin/splotch uses the
+    # path: counts of Ge genes (page-locked host memory) -> Batch (H2D) -> Sampler -> warm-up + sampling
+    # transitions from initialisation -> draws of the non-spot block + posterior summaries of every spot (D2H
+    # into page-locked host arrays).  The page-locked buffers are allocated once, outside the timed region.
     Ge = args.e2e_genes or min(G, 1184 if N < 10000 else 148)
-    e2e_iters = 10 if N < 10000 else 4
-    counts_host = np.ascontiguousarray(genes["counts"][:Ge])
+    e2e_iters = args.e2e_iters or (50 if N < 10000 else 8)
+    e_warm, e_samp = e2e_iters // 2, e2e_iters - e2e_iters // 2
+    counts_host = api.pinned_empty((Ge, N), np.int32)
+    counts_host[...] = genes["counts"][:Ge]
     pm = genes["beta_prior_mean"][:Ge] if "beta_prior_mean" in genes else None
     ps = genes["beta_prior_std"][:Ge] if "beta_prior_std" in genes else None
+    out_summ = api.pinned_empty((6, Ge, N))
+    out_draws = (api.pinned_empty((Ge, args.chains, e_samp, 7)), api.pinned_empty((Ge, args.chains, e_samp, model.n_small)),
+                 api.pinned_empty((Ge, args.chains), np.int32))
 
     def e2e_step():
         b = api.Batch(model, counts_host, pm, ps, gene_id0=rank * G)       # H2D of this step's inputs
-        s = api.Sampler(b, api.nuts_cfg(e2e_iters // 2, e2e_iters - e2e_iters // 2, args.chains, seed=7))
+        s = api.Sampler(b, api.nuts_cfg(e_warm, e_samp, args.chains, seed=7))
         s.run()
-        diag, small, nd = s.draws()                                       # D2H of the step's results
-        summ = s.spot_summaries()
+        diag, small, nd = s.draws(out=out_draws)                          # D2H of the step's results
+        summ = s.spot_summaries(out=out_summ)
         cnt = s.counters()
+        assert int(nd.min()) == e_samp and np.isfinite(summ["lambda/mean"]).all()
         d2h = diag.nbytes + small.nbytes + nd.nbytes + sum(v.nbytes for v in summ.values())
         s.close(); b.close()
-        return cnt["n_grad"], counts_host.nbytes + (pm.nbytes + ps.nbytes if pm is not None else 0), d2h
+        return cnt["n_grad"], counts_host.nbytes + (pm.nbytes + ps.nbytes if pm is not None else 0), d2h, cnt["n_launches"]
 
     e2e_step()
     barrier()
     t0 = time.time()
-    e_grads, h2d, d2h = 0, 0, 0
+    e_grads, h2d, d2h, e_launches = 0, 0, 0, 0
     e_steps = max(2, min(args.steps, 4))
     for _ in range(e_steps):
-        g, a, b_ = e2e_step()
-        e_grads += g; h2d = a; d2h = b_
+        g, a, b_, nl = e2e_step()
+        e_grads += g; h2d = a; d2h = b_; e_launches += nl
     barrier()
     e_dt = time.time() - t0
 
@@ -314,8 +325,9 @@ def main():
                        "phase": "Stan warm-up transitions %d..%d of every chain (adaptive NUTS, max_depth 10)"
                                 % (args.warmup * iters, total_iters)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": "%d genes x %d chains: Batch(host counts) -> Sampler %d transitions -> draws + spot "
-                            "summaries to host, per step, through the C ABI" % (Ge, args.chains, e2e_iters)},
+                    "what": "%d genes x %d chains per step: Batch(host counts) -> Sampler, %d warm-up + %d sampling "
+                            "transitions from initialisation -> draws + spot summaries to host, through the C ABI; "
+                            "wall clock, %d steps" % (Ge, args.chains, e_warm, e_samp, e_steps)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_nuts_advance",

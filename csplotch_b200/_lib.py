@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcsplotch_b200.so")
+# CSPLOTCH_LIB: another build of the same library (development builds of csplotch_b200.build --dev)
+LIB_PATH = os.environ.get("CSPLOTCH_LIB") or os.path.join(HERE, "libcsplotch_b200.so")
 
 
 class CsplotchError(RuntimeError):
@@ -51,7 +52,7 @@ SYMBOLS = [
     "csplotch_nuts_cfg_default", "csplotch_sampler_create", "csplotch_sampler_destroy", "csplotch_sampler_init",
     "csplotch_sampler_advance", "csplotch_sampler_sync", "csplotch_sampler_last_ms", "csplotch_sampler_counters",
     "csplotch_sampler_status", "csplotch_sampler_profile", "csplotch_sampler_get_draws", "csplotch_sampler_get_theta_draws",
-    "csplotch_sampler_get_state", "csplotch_sampler_get_spot_summaries",
+    "csplotch_sampler_get_state", "csplotch_sampler_get_spot_summaries", "csplotch_rdump_read_genes", "csplotch_host_alloc", "csplotch_host_free",
 ]
 
 _lib = None

@@ -49,6 +49,36 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
+class _PinnedOwner:
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.csplotch_host_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (csplotch_host_alloc); freed with the array.  Use it for counts
+    handed to Batch and as `out=` of Sampler.draws / spot_summaries: transfers then run at PCIe speed."""
+    lib = _lib.lib()
+    _lib.require_gpu()
+    shape = (shape,) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    if nbytes == 0:
+        return np.empty(shape, dtype=dt)
+    p = C.c_void_p()
+    check(lib.csplotch_host_alloc(C.c_uint64(nbytes), C.byref(p)))
+    buf = (C.c_ubyte * nbytes).from_address(p.value)
+    buf._owner = _PinnedOwner(lib, p.value)       # arr.base -> buf -> owner: freed when the last view dies
+    return np.frombuffer(buf, dtype=dt).reshape(shape)
+
+
 class Model:
     """Gene-shared covariates (the data{} block minus `counts`, `beta_prior_*`) resident on the GPU."""
 
@@ -308,12 +338,19 @@ class Sampler:
         check(self.lib.csplotch_sampler_status(self.h, _p(st), _p(it)))
         return st, it
 
-    def draws(self):
-        """(diag [G,ch,S,7], small [G,ch,S,n_small] unconstrained beta_raw|scalars, n_draws [G,ch])"""
+    def draws(self, out=None):
+        """(diag [G,ch,S,7], small [G,ch,S,n_small] unconstrained beta_raw|scalars, n_draws [G,ch]);
+        `out`: that triple preallocated (e.g. `pinned_empty`), filled in place"""
         ns = self.cfg.num_samples
-        diag = np.empty((self.G, self.nch, ns, 7))
-        small = np.empty((self.G, self.nch, ns, self.model.n_small))
-        nd = np.zeros((self.G, self.nch), dtype=np.int32)
+        if out is not None:
+            diag, small, nd = out
+            assert diag.shape == (self.G, self.nch, ns, 7) and small.shape == (self.G, self.nch, ns, self.model.n_small)
+            assert nd.shape == (self.G, self.nch) and nd.dtype == np.int32 and diag.dtype == small.dtype == np.float64
+            assert diag.flags.c_contiguous and small.flags.c_contiguous and nd.flags.c_contiguous
+        else:
+            diag = np.empty((self.G, self.nch, ns, 7))
+            small = np.empty((self.G, self.nch, ns, self.model.n_small))
+            nd = np.zeros((self.G, self.nch), dtype=np.int32)
         check(self.lib.csplotch_sampler_get_draws(self.h, _p(diag), _p(small), _p(nd)))
         return diag, small, nd
 
@@ -329,10 +366,15 @@ class Sampler:
         check(self.lib.csplotch_sampler_get_state(self.h, _p(th), _p(eps), _p(mi)))
         return th, eps, mi
 
-    def spot_summaries(self):
-        """dict of (G, N) arrays: mean/std (ddof=0, pooled over chains) of log_lambda, lambda, psi."""
+    def spot_summaries(self, out=None):
+        """dict of (G, N) arrays: mean/std (ddof=0, pooled over chains) of log_lambda, lambda, psi.
+        `out`: a preallocated float64 array (6, G, N) (e.g. `pinned_empty`) the six results are views of"""
         N = self.model.N
-        arrs = [np.empty((self.G, N)) for _ in range(6)]
+        if out is not None:
+            assert out.shape == (6, self.G, N) and out.dtype == np.float64 and out.flags.c_contiguous
+            arrs = [out[i] for i in range(6)]
+        else:
+            arrs = [np.empty((self.G, N)) for _ in range(6)]
         check(self.lib.csplotch_sampler_get_spot_summaries(self.h, *[_p(a) for a in arrs]))
         keys = ["log_lambda/mean", "log_lambda/std", "lambda/mean", "lambda/std", "psi/mean", "psi/std"]
         out = dict(zip(keys, arrs))

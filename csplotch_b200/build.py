@@ -8,7 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "csplotch.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("device_ops.cuh", "nuts_core.h", "philox.h")] + [
+HOST_SRC = os.path.join(HERE, "csrc", "ingest.cpp")   # host-only part of the ABI (R-dump fast path)
+DEPS = [SRC, HOST_SRC] + [os.path.join(HERE, "csrc", f) for f in ("device_ops.cuh", "nuts_core.h", "philox.h")] + [
     os.path.join(ROOT, "include", "csplotch.h")]
 OUT = os.path.join(HERE, "libcsplotch_b200.so")
 
@@ -34,13 +35,20 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+DEV_OUT = os.path.join(HERE, "libcsplotch_b200_dev.so")
+
+
+def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
+    """dev=True: K in {1, 10} only, written to libcsplotch_b200_dev.so (experiments; load it with
+    CSPLOTCH_LIB=<path>); the product library always holds every instantiation."""
+    if not dev and not force and not is_stale():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    out = DEV_OUT if dev else OUT
+    cmd = ([nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DCSPLOTCH_DEV_KT"] if dev else [])
+           + ["-o", out, SRC, HOST_SRC])
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, dev="--dev" in sys.argv))

@@ -45,20 +45,13 @@ def data_path(data_dir: str, g: int) -> str:
 
 
 def load_genes(data_dir: str, gene_ids):
-    """Shared covariates parsed once; only counts / beta priors from every other file."""
+    """Shared covariates parsed once (first file); `counts` / beta priors of every gene by the library's
+    native tail reader, all host cores (csplotch_rdump_read_genes)."""
     first = rdump.read_rdump(data_path(data_dir, gene_ids[0]))
     shared = {k: v for k, v in first.items() if k not in rdump.GENE_KEYS}
-    counts, pm, ps = [], [], []
-    for i, g in enumerate(gene_ids):
-        d = first if i == 0 else rdump.read_rdump_gene_only(data_path(data_dir, g))
-        counts.append(np.asarray(d["counts"], dtype=np.int32))
-        if "beta_prior_mean" in d:
-            pm.append(np.asarray(d["beta_prior_mean"], dtype=np.float64))
-            ps.append(np.asarray(d["beta_prior_std"], dtype=np.float64))
-    genes = {"counts": np.stack(counts)}
-    if pm:
-        genes["beta_prior_mean"] = np.stack(pm)
-        genes["beta_prior_std"] = np.stack(ps)
+    n_spots = int(np.sum(first["N_spots"]))
+    K = int(np.size(first["beta_prior_mean"])) if "beta_prior_mean" in first else 0
+    genes = rdump.read_genes_native([data_path(data_dir, g) for g in gene_ids], n_spots, K)
     return shared, genes
 
 

@@ -31,6 +31,8 @@ static int fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
 }
+// host-only translation units of this library (ingest.cpp) report errors through the same thread-local message
+extern "C" int csplotch_internal_fail(int code, const char *msg) { return fail(code, msg ? msg : ""); }
 #define CU_TRY(expr)                                                                              \
   do {                                                                                            \
     cudaError_t e__ = (expr);                                                                     \
@@ -376,6 +378,25 @@ k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ Sa
 // host: model
 // ------------------------------------------------------------------------------------------------
 extern "C" const char *csplotch_last_error(void) { return g_err.c_str(); }
+
+// page-locked host memory for the caller's input / result arrays: cudaMemcpy to or from such a buffer is one
+// DMA at PCIe speed instead of a staged copy through the driver's bounce buffers (pageable numpy arrays
+// arrive at ~2 GB/s: as long as sampling itself for the 1.4 GB of spot summaries of the c2 gene list)
+extern "C" int32_t csplotch_host_alloc(uint64_t bytes, void **out) {
+  if (!out) return fail(CSPLOTCH_E_INVALID, "null argument");
+  *out = nullptr;
+  if (bytes == 0) return CSPLOTCH_OK;
+  if (cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return fail(CSPLOTCH_E_NOMEM, "cudaHostAlloc failed (no device, or not enough lockable host memory)");
+  }
+  return CSPLOTCH_OK;
+}
+extern "C" int32_t csplotch_host_free(void *p) {
+  if (p) CU_TRY(cudaFreeHost(p));
+  return CSPLOTCH_OK;
+}
 extern "C" int32_t csplotch_abi_version(void) { return CSPLOTCH_ABI_VERSION; }
 extern "C" int32_t csplotch_device_count(void) {
   int n = 0;
@@ -759,6 +780,16 @@ static int sm_count() {
   return n > 0 ? n : 148;
 }
 
+#ifdef CSPLOTCH_DEV_KT
+// development builds (python -m csplotch_b200.build --dev): only the two instantiations the named configs use,
+// a quarter of the compile time; never shipped (separate output file, loaded only through CSPLOTCH_LIB)
+#define DISPATCH_KT(kt, ...)                 \
+  switch (kt) {                               \
+    case 1: { constexpr int KT = 1; __VA_ARGS__; } break;   \
+    case 10: { constexpr int KT = 10; __VA_ARGS__; } break; \
+    default: return fail(CSPLOTCH_E_UNSUPPORTED, "development build: N_celltypes in {1, 10} only"); \
+  }
+#else
 #define DISPATCH_KT(kt, ...)                 \
   switch (kt) {                               \
     case 1: { constexpr int KT = 1; __VA_ARGS__; } break;   \
@@ -773,6 +804,7 @@ static int sm_count() {
     case 16: { constexpr int KT = 16; __VA_ARGS__; } break; \
     default: return fail(CSPLOTCH_E_UNSUPPORTED, "unsupported N_celltypes"); \
   }
+#endif
 
 template <class Kern>
 static cudaError_t set_smem(Kern kern, size_t bytes) {

@@ -16,6 +16,7 @@ whose shared covariates are already known.
 """
 from __future__ import annotations
 
+import os
 import re
 
 import numpy as np
@@ -71,6 +72,30 @@ def read_rdump(filename: str, keys=None) -> dict:
 def read_rdump_gene_only(filename: str) -> dict:
     """Fast path: only the keys that differ between genes (bin/splotch_generate_input_files:329-346)."""
     return read_rdump(filename, keys=GENE_KEYS)
+
+
+def read_genes_native(paths, n_spots: int, n_celltypes: int = 0, n_threads: int = 0):
+    """`counts` [G, N] (and `beta_prior_mean`, `beta_prior_std` [G, K] when n_celltypes > 0) of many data_<g>.R
+    files through the library's native reader (csplotch_rdump_read_genes, csrc/ingest.cpp): host threads, one
+    file each, only the tail of every file is read.  Same values as `read_rdump_gene_only` file by file."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.lib()
+    G = len(paths)
+    counts = np.empty((G, n_spots), dtype=np.int32)
+    pm = ps = None
+    if n_celltypes > 0:
+        pm = np.empty((G, n_celltypes))
+        ps = np.empty((G, n_celltypes))
+    arr = (C.c_char_p * G)(*[os.fsencode(p) for p in paths])
+    vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None  # noqa: E731
+    _lib.check(lib.csplotch_rdump_read_genes(arr, C.c_int32(G), C.c_int32(n_spots), C.c_int32(n_celltypes),
+                                            vp(counts), vp(pm), vp(ps), C.c_int32(n_threads)))
+    out = {"counts": counts}
+    if pm is not None:
+        out["beta_prior_mean"], out["beta_prior_std"] = pm, ps
+    return out
 
 
 def _fmt(v) -> str:

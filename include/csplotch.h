@@ -116,6 +116,12 @@ int32_t csplotch_abi_version(void);
 int32_t csplotch_device_count(void);
 int32_t csplotch_set_device(int32_t device);
 
+/* Page-locked host buffers for arrays handed to / filled by the calls below (optional: every host pointer may
+ * also be ordinary pageable memory).  The reference moves these data through files and pipes; here they cross
+ * PCIe, and a pinned buffer makes each transfer a single DMA.  csplotch_host_free(NULL) is a no-op. */
+int32_t csplotch_host_alloc(uint64_t bytes, void **out);
+int32_t csplotch_host_free(void *p);
+
 /* ---- data{} + transformed data{} (stan/splotch_stan_model.stan:20-72) ---------------- */
 int32_t csplotch_model_create(const csplotch_shared_desc *desc, csplotch_model **out);
 void csplotch_model_destroy(csplotch_model *m);
@@ -191,6 +197,16 @@ int32_t csplotch_sampler_get_state(csplotch_sampler *s, double *theta, double *s
 int32_t csplotch_sampler_get_spot_summaries(csplotch_sampler *s, double *log_lambda_mean,
                                             double *log_lambda_std, double *lambda_mean, double *lambda_std,
                                             double *psi_mean, double *psi_std);
+
+/* ---- ingestion fast path ------------------------------------------------------
+ * Stands in for read_rdump (/root/reference/splotch/utils.py:78-111) on the per-gene part of the
+ * `data_<g>.R` files that bin/splotch_generate_input_files:329-346 writes: only `counts` (and, for
+ * comp_splotch_stan_model, `beta_prior_mean` / `beta_prior_std`) differ between genes and to_rdump writes them
+ * last, so only the tail of every file is read and parsed, n_threads files at a time (0 = all host cores).
+ * paths[G]; counts[G][N]; beta_prior_mean/std [G][K] or both NULL.  Fails (CSPLOTCH_E_INVALID, message names the
+ * file) on a missing file or key, a non-integer count, or a length other than N / K.  Host only, no device. */
+int32_t csplotch_rdump_read_genes(const char *const *paths, int32_t G, int32_t N, int32_t K, int32_t *counts,
+                                  double *beta_prior_mean, double *beta_prior_std, int32_t n_threads);
 
 #ifdef __cplusplus
 }

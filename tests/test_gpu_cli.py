@@ -142,3 +142,29 @@ def test_error_behaviour(golden_dir):
     s.run()
     st, it = s.status()
     assert st[0, 0] == 1 and it[0, 0] == 0 and (st.reshape(-1)[1:] == 0).all() and (it.reshape(-1)[1:] == 10).all()
+
+
+def test_pinned_buffers_give_the_same_results():
+    """Page-locked input / output arrays (csplotch_host_alloc) are a transfer optimisation only."""
+    shared = synth.shared_tiny(seed=3)
+    genes = synth.simulate_counts(shared, 5, 11)
+    model = api.Model(shared, "comp_splotch_stan_model")
+    cfg = api.nuts_cfg(15, 10, 2, seed=4)
+    b0 = api.Batch(model, genes["counts"], genes["beta_prior_mean"], genes["beta_prior_std"])
+    s0 = api.Sampler(b0, cfg).run()
+    want_draws, want_summ = s0.draws(), s0.spot_summaries()
+    counts = api.pinned_empty(genes["counts"].shape, np.int32)
+    counts[...] = genes["counts"]
+    b1 = api.Batch(model, counts, genes["beta_prior_mean"], genes["beta_prior_std"])
+    s1 = api.Sampler(b1, cfg).run()
+    out = (api.pinned_empty(want_draws[0].shape), api.pinned_empty(want_draws[1].shape),
+           api.pinned_empty(want_draws[2].shape, np.int32))
+    got_draws = s1.draws(out=out)
+    summ_buf = api.pinned_empty((6, 5, model.N))
+    got_summ = s1.spot_summaries(out=summ_buf)
+    for a, b in zip(want_draws, got_draws):
+        assert np.array_equal(a, b)
+    assert got_draws[0] is out[0]
+    for k in want_summ:
+        assert np.array_equal(want_summ[k], got_summ[k])
+    del out, got_draws, summ_buf, got_summ, counts          # frees the page-locked memory with the last view
