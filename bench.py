@@ -149,7 +149,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    family, shared, genes = make_inputs(args.workload, max(8, (os.cpu_count() or 8) // 4), 0)
+    # the same genes as the cpu_baseline leg of the GPU arm: the head of the workload's gene list
+    family, shared, genes = make_inputs(args.workload, WORKLOADS[args.workload][1], 0)
     nthr = os.cpu_count() or 1
     N = int(np.sum(shared["N_spots"]))
     iters = args.cpu_iters or cpu_iters_for(family, shared, genes, nthr, 120.0 / max(1, args.steps + args.warmup))

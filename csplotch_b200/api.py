@@ -193,6 +193,76 @@ class Model:
         return cols
 
 
+def param_layout(model: "Model"):
+    """[(name, theta_index, transform)] of every parameter in the order of the unconstrained vector (include/csplotch.h:
+    psi | beta_raw | tau | a | sigma | sigma_level_2 | sigma_level_3 | theta | phi | noise_raw; beta_raw[i, j] at i + L*j,
+    for comp_splotch_stan_model beta_raw[i, j, k] at (i*C + j)*K + k).  Names are the dotted CSV column names."""
+    L = sum(model.levels)
+    N, Cc, K = model.N, model.C, model.K
+    out, o = [], 0
+    if model.car:
+        out += [("psi.%d" % (i + 1), o + i, "id") for i in range(N)]
+        o += N
+    if model.family == 1:
+        out += [("beta_raw.%d.%d.%d" % (i + 1, j + 1, k + 1), o + (i * Cc + j) * K + k, "id")
+                for i in range(L) for j in range(Cc) for k in range(K)]
+    else:
+        out += [("beta_raw.%d.%d" % (i + 1, j + 1), o + i + L * j, "id") for j in range(Cc) for i in range(L)]
+    o += L * Cc * K
+    scal = ([("tau.1", "log"), ("a.1", "logit")] if model.car else []) + [("sigma", "log")]
+    scal += [("sigma_level_2.1", "log")] if model.levels[1] else []
+    scal += [("sigma_level_3.1", "log")] if model.levels[2] else []
+    scal += [("theta.1", "logit")] if model.zi else []
+    scal += [("phi.1", "logphi")] if model.nb else []
+    for name, tr in scal:
+        out.append((name, o, tr))
+        o += 1
+    out += [("noise_raw.%d" % (i + 1), o + i, "id") for i in range(N)]
+    o += N
+    assert o == model.dim
+    return out
+
+
+def unconstrain(model: "Model", init: dict, radius: float = 2.0, seed: int = 0) -> np.ndarray:
+    """CmdStan `init=FILE.json` -> unconstrained theta.  `init` maps parameter names to CONSTRAINED values, either by
+    dotted CSV column name (the files bin/splotch_vinit:177-182 writes from a Pathfinder draw) or by variable name with
+    (nested) arrays as in CmdStan's JSON format.  Non-parameter keys (log_lambda.*, beta_level_*, lp__) are ignored;
+    parameters that are absent start uniform(-radius, radius) on the unconstrained scale, as in Stan."""
+    flat = {}
+
+    def walk(prefix, v):
+        if isinstance(v, (list, tuple, np.ndarray)):
+            for i, x in enumerate(v):
+                walk("%s.%d" % (prefix, i + 1), x)
+        else:
+            flat[prefix] = float(v)
+
+    for k, v in init.items():
+        walk(str(k).strip(), v)
+    rng = np.random.default_rng(seed)
+    theta = rng.uniform(-radius, radius, model.dim)
+    for name, idx, tr in param_layout(model):
+        v = flat.get(name)
+        if v is None and name.endswith(".1"):
+            v = flat.get(name[:-2])        # scalars declared as real x[1]: "tau" or "tau.1"
+        if v is None:
+            continue
+        if tr == "log":
+            if not v > 0:
+                raise CsplotchError("init: %s must be positive, got %r" % (name, v))
+            v = np.log(v)
+        elif tr == "logit":
+            if not 0 < v < 1:
+                raise CsplotchError("init: %s must lie in (0, 1), got %r" % (name, v))
+            v = np.log(v) - np.log1p(-v)
+        elif tr == "logphi":
+            if not v > 1e-6:
+                raise CsplotchError("init: %s must exceed 1e-6, got %r" % (name, v))
+            v = np.log(v - 1e-6)
+        theta[idx] = v
+    return theta
+
+
 class Batch:
     """counts (+ beta priors) of G genes on the GPU.  counts: (G, N) int; priors: (G, K) for comp."""
 

@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
     if not dev and not force and not is_stale():
         return OUT
     out = DEV_OUT if dev else OUT
-    cmd = ([nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DCSPLOTCH_DEV_KT"] if dev else [])
+    cmd = ([nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DCSPLOTCH_DEV_KT"] + os.environ.get("CSPLOTCH_DEV_DEFS", "").split() if dev else [])
            + ["-o", out, SRC, HOST_SRC])
     subprocess.check_call(cmd)
     return out

@@ -173,7 +173,20 @@ def cmdstan_shim(argv=None, family=None):
                       data.get("beta_prior_std") if fam == 1 else None)
     # one chain per process like CmdStan; chain ids start at 1, so run chain_id chains' worth of keying
     cfg = api.nuts_cfg(num_warmup, num_samples, 1, seed=seed + 7919 * (chain_id - 1), keep_draws=True)
-    s = api.Sampler(batch, cfg).run(chunk=50)
+    # init=FILE.json: constrained starting values (bin/splotch_vinit:194); init=R: radius of the uniform start
+    theta_init = None
+    if "init" in kv:
+        try:
+            cfg.init_radius = float(kv["init"])
+        except ValueError:
+            import json
+            try:
+                with open(kv["init"]) as f:
+                    theta_init = api.unconstrain(model, json.load(f), radius=cfg.init_radius, seed=cfg.seed)[None, None, :]
+            except (OSError, ValueError, api.CsplotchError) as e:
+                print("Error reading init file %s: %s" % (kv["init"], e), file=sys.stderr)
+                return 1
+    s = api.Sampler(batch, cfg, theta_init=theta_init).run(chunk=50)
     st, _ = s.status()
     if (st != 0).any():
         return 1

@@ -369,6 +369,10 @@ k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ Sa
       cs.cyc_eval += ops.cyc_eval; cs.cyc_merge += ops.cyc_merge; cs.cyc_copy += ops.cyc_copy;
       cs.n_merge += ops.n_merge; cs.n_copy += ops.n_copy; cs.cyc_pro += ops.cyc_pro; cs.cyc_fin += ops.cyc_fin;
       cs.cyc_other += (clock64() - t_chain) - ops.cyc_eval - ops.cyc_merge - ops.cyc_copy;
+#ifdef CSPLOTCH_PROF_WAITS
+      cs.cyc_merge = ops.w_issue; cs.cyc_copy = ops.w_rest; cs.cyc_other = ops.w_ring; cs.n_merge = ops.w_rel; cs.n_copy = ops.w_bins;
+      cs.cyc_pro = ops.w_pre; cs.cyc_fin = ops.w_post; cs.cyc_eval = ops.cyc_eval; cs.n_grad_total = cs.n_grad_total;
+#endif
       s.cs[w] = cs;
     }
   }
@@ -649,7 +653,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   }
   std::vector<int> rowptr(N + 1, 0), col;
   std::vector<unsigned short> ell;
-  std::vector<double> eigu, eigm;
+  std::vector<double> eigu, eigm, eigg, eiggm;
   if (car) {
     const int ring_n = (dm.look == 1 ? 4 : 8) * kTile;
     if (tiled) ell.assign((size_t)dm.NT * dm.ell_w * kTile, (unsigned short)ring_n);
@@ -668,6 +672,18 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     for (int i = 0; i < N; ++i) mult[d->eig_values[i]] += 1.0;
     for (auto &kv : mult) { eigu.push_back(kv.first); eigm.push_back(kv.second); }
     dm.n_eig = (int)eigu.size();
+    // groups of kEigGroup eigenvalues with the same multiplicity (eig_group_terms): one log and one division each
+    std::vector<std::pair<double, double>> by_mult;  // (multiplicity, eigenvalue)
+    for (auto &kv : mult) by_mult.emplace_back(kv.second, kv.first);
+    std::sort(by_mult.begin(), by_mult.end());
+    for (size_t i = 0; i < by_mult.size();) {
+      const double mlt = by_mult[i].first;
+      int cnt = 0;
+      for (; i < by_mult.size() && by_mult[i].first == mlt && cnt < kEigGroup; ++i, ++cnt) eigg.push_back(by_mult[i].second);
+      for (; cnt < kEigGroup; ++cnt) eigg.push_back(0.0);  // u = 1: contributes nothing to either sum
+      eiggm.push_back(mlt);
+    }
+    dm.n_eigg = (int)eiggm.size();
   }
   std::vector<double> E;
   if (d->family == CSPLOTCH_COMP_SPLOTCH) {
@@ -677,7 +693,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
         E[((size_t)(ji / kTile) * kt + k) * kTile + (ji % kTile)] = d->E[(size_t)m->perm[ji] * K + k];
   }
   bool ok = true;
-  double *p_lsf, *p_E, *p_eu, *p_em;
+  double *p_lsf, *p_E, *p_eu, *p_em, *p_eg, *p_egm;
   int *p_key, *p_rp, *p_col, *p_m2, *p_m3, *p_imap;
   unsigned short *p_ell;
   ok &= m->buf.upload(&p_lsf, lsf) == cudaSuccess;
@@ -688,6 +704,8 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
   ok &= m->buf.upload(&p_E, E) == cudaSuccess;
   ok &= m->buf.upload(&p_eu, eigu) == cudaSuccess;
   ok &= m->buf.upload(&p_em, eigm) == cudaSuccess;
+  ok &= m->buf.upload(&p_eg, eigg) == cudaSuccess;
+  ok &= m->buf.upload(&p_egm, eiggm) == cudaSuccess;
   ok &= m->buf.upload(&p_m2, map2) == cudaSuccess;
   ok &= m->buf.upload(&p_m3, map3) == cudaSuccess;
   ok &= m->buf.upload(&p_imap, m->imap) == cudaSuccess;
@@ -696,7 +714,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     delete m;
     return fail(CSPLOTCH_E_CUDA, "model upload failed: " + msg);
   }
-  dm.lsf = p_lsf; dm.key = p_key; dm.rowptr = p_rp; dm.col = p_col; dm.ell = p_ell; dm.E = p_E; dm.eigu = p_eu; dm.eigm = p_em;
+  dm.lsf = p_lsf; dm.key = p_key; dm.rowptr = p_rp; dm.col = p_col; dm.ell = p_ell; dm.E = p_E; dm.eigu = p_eu; dm.eigm = p_em; dm.eigg = p_eg; dm.eiggm = p_egm;
   dm.map2 = p_m2; dm.map3 = p_m3; dm.imap = p_imap;
   *out = m;
   return CSPLOTCH_OK;

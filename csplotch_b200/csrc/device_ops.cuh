@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fastmath.h"
 #include "nuts_core.h"
 
 namespace csp {
@@ -27,6 +28,35 @@ constexpr int kWarps = kBlock / 32;
 constexpr int kRedMax = 12;  // doubles per block reduction
 constexpr int kTile = kBlock;    // spots per tile of the staged pipeline: thread t <-> spot t of the tile
 constexpr int kMaxEll = 8;       // widest ELL adjacency the tiled path takes (Visium hex: 6, ST / HD grid: 4)
+// The CAR log-determinant sum_i m_i log(1 - a lambda_i) and its derivative in a, -sum_i m_i lambda_i / (1 - a lambda_i),
+// over GROUPS of eight eigenvalues of equal multiplicity: with u_i = 1 - a lambda_i in (0, 2],
+//   sum_i log u_i = log(prod u_i)          and          sum_i lambda_i / u_i = (sum_i lambda_i prod_{l != i} u_l) / prod u_i,
+// so a group costs ONE log and ONE division (and a depth-3 product tree) instead of eight log1p and eight divisions
+// -- fp64 log1p alone is ~250 instructions on this GPU, more than the rest of a spot's work, and ST / HD designs
+// have about as many distinct eigenvalues as spots.  prod u_i stays within [(1-a)^8, 256]: no over/underflow for
+// any a the sampler can reach short of a == 1 (then log 0 = -inf as before); relative error of the product 8 ulp,
+// i.e. ~1e-15 absolute per group in the log.
+constexpr int kEigGroup = 8;
+__device__ __forceinline__ void eig_group_terms(const double *__restrict__ lam8, double mult, double a, double &ldet,
+                                                double &dldet) {
+  const double2 l01 = __ldg(reinterpret_cast<const double2 *>(lam8));
+  const double2 l23 = __ldg(reinterpret_cast<const double2 *>(lam8) + 1);
+  const double2 l45 = __ldg(reinterpret_cast<const double2 *>(lam8) + 2);
+  const double2 l67 = __ldg(reinterpret_cast<const double2 *>(lam8) + 3);
+  const double lam[8] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y, l67.x, l67.y};
+  double p[4], sn[4];  // per pair: product of u, sum_i lambda_i prod_{l != i} u_l
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double u0 = fma(-a, lam[2 * i], 1.0), u1 = fma(-a, lam[2 * i + 1], 1.0);
+    p[i] = u0 * u1;
+    sn[i] = fma(lam[2 * i], u1, lam[2 * i + 1] * u0);
+  }
+  const double pa = p[0] * p[1], sa = fma(sn[0], p[1], sn[1] * p[0]);
+  const double pb = p[2] * p[3], sb = fma(sn[2], p[3], sn[3] * p[2]);
+  const double P = pa * pb, S = fma(sa, pb, sb * pa);
+  ldet += mult * log(P);
+  dldet -= mult * (S / P);
+}
 
 struct DevModel {
   int family, N, Npad, C, K, L1, L2, L3, L, bot0, nbeta, nscal, nsmall, nsmall_pad;
@@ -52,6 +82,9 @@ struct DevModel {
   const double *E;       // [NT][K][kTile]  (tile-major, cell type, spot-in-tile): coalesced per k
   const double *eigu;    // [n_eig] distinct eigenvalues
   const double *eigm;    // [n_eig] multiplicities
+  int n_eigg;            // groups of kEigGroup distinct eigenvalues of equal multiplicity (padded with lambda = 0)
+  const double *eigg;    // [n_eigg][kEigGroup]
+  const double *eiggm;   // [n_eigg] the multiplicity of each group
   const int *map2;       // [L2] 0-based level-1 row of each level-2 row
   const int *map3;       // [L3] 0-based level-2 row of each level-3 row
   const int *imap;       // [Di] internal index -> Stan index (-1 = padding)
@@ -251,6 +284,18 @@ struct DevOps {
   double *out_theta;  // [num_samples][D] Stan order
   double *out_summ;   // [6][N]: mean,M2 of log_lambda | mean,M2 of lambda | mean,M2 of psi
   long long cyc_eval = 0, cyc_merge = 0, cyc_copy = 0, cyc_other = 0, n_merge = 0, n_copy = 0, cyc_pro = 0, cyc_fin = 0;
+#ifdef CSPLOTCH_PROF_WAITS
+  // development instrumentation: cycles thread 0 spends in each wait of the tile loop (reported through the
+  // profile slots of merge / copy / other / n_merge / n_copy by k_nuts_advance)
+  long long w_psi = 0, w_rest = 0, w_ring = 0, w_rel = 0, w_bins = 0, w_issue = 0, w_pre = 0, w_post = 0, w_t = 0;
+#define PWMARK(var) { const long long n__ = clock64(); var += n__ - w_t; w_t = n__; }
+#define PWSTART() { w_t = clock64(); }
+#define PW(var, ...) { const long long t__ = clock64(); __VA_ARGS__; var += clock64() - t__; }
+#else
+#define PW(var, ...) { __VA_ARGS__; }
+#define PWMARK(var) {}
+#define PWSTART() {}
+#endif
 
   __device__ __forceinline__ DevOps(const DevModel &mm) : m(mm) {}
 
@@ -360,12 +405,8 @@ struct DevOps {
     // log-determinant term of the CAR prior over the distinct eigenvalues (the tiled pass folds it into
     // its tile loop, where it is independent work that fills stall slots)
     if (m.car && !eig_done) {
-      for (int i = tid; i < m.n_eig; i += kBlock) {
-        const double lam = m.eigu[i], mult = m.eigm[i];
-        const double x = sc.a * lam;
-        a_ldet += mult * log1p(-x);
-        a_dldet += mult * (-lam / (1.0 - x));
-      }
+      for (int i = tid; i < m.n_eigg; i += kBlock)
+        eig_group_terms(m.eigg + (size_t)i * kEigGroup, __ldg(m.eiggm + i), sc.a, a_ldet, a_dldet);
     }
     // beta_raw ~ normal(0,1)
     const double *sb = dq + m.o_small;
@@ -562,29 +603,40 @@ struct DevOps {
   // psi inputs run look+1 tiles ahead (the drift of tile k+look precedes the gradient of tile k, which
   // still reads p, g, minv of its own tile) in look+2 slots; the rest one tile ahead in two slots.  Called
   // by every lane of warp 0 at trip k: issues psi(k+look+1) and rest(k+1).
+  // copy number d of the table: psi streams go to tile k+look+1, the rest to tile k+1
   template <int LOOK>
-  static __device__ __forceinline__ void issue_tiles(const TileCtx &c, int k) {
+  static __device__ __forceinline__ void issue_desc(const TileCtx &c, int k, int di) {
     constexpr uint32_t NPS = LOOK + 2;
-    const int lane = threadIdx.x;  // warp 0: lane == tid
-    const int kp = k + LOOK + 1;  // psi tile issued at trip k
-    if (lane == 0 && c.car && kp >= 0 && kp < c.NT)
-      mbar_expect_tx(c.mbar + ((c.seq0 + (uint32_t)kp) % NPS), c.psi_tx);
-    if (lane == 1 && k + 1 >= 0 && k + 1 < c.NT)
-      mbar_expect_tx(c.mbar + 4 + ((c.seq0 + (uint32_t)(k + 1)) & 1u), c.rest_tx);
-    __syncwarp();
-    if (lane < c.n_desc) {
-      const TmaDesc d = c.desc[lane];
-      const int tile = d.group == 0 ? kp : k + 1;
-      if (tile >= 0 && tile < c.NT) {
-        const uint32_t seq = c.seq0 + (uint32_t)tile;
-        const uint32_t slot = d.group == 0 ? seq % NPS : (seq & 1u);
-        unsigned char *dst = d.group == 0
-                                 ? reinterpret_cast<unsigned char *>(smem_d + c.psi_o) + slot * (4 * kTile * sizeof(double))
-                                 : reinterpret_cast<unsigned char *>(smem_d + c.rest_o) + (size_t)slot * c.stage_bytes;
-        bulk_g2s(dst + d.dst_off, d.src + (size_t)tile * d.tile_bytes, d.tile_bytes, c.mbar + 4 * d.group + slot);
-      }
+    const TmaDesc d = c.desc[di];
+    const int tile = d.group == 0 ? k + LOOK + 1 : k + 1;
+    if (tile >= 0 && tile < c.NT) {
+      const uint32_t seq = c.seq0 + (uint32_t)tile;
+      const uint32_t slot = d.group == 0 ? seq % NPS : (seq & 1u);
+      unsigned char *dst = d.group == 0
+                               ? reinterpret_cast<unsigned char *>(smem_d + c.psi_o) + slot * (4 * kTile * sizeof(double))
+                               : reinterpret_cast<unsigned char *>(smem_d + c.rest_o) + (size_t)slot * c.stage_bytes;
+      bulk_g2s(dst + d.dst_off, d.src + (size_t)tile * d.tile_bytes, d.tile_bytes, c.mbar + 4 * d.group + slot);
     }
   }
+  template <int LOOK>
+  static __device__ __forceinline__ void expect_tiles(const TileCtx &c, int k, bool psi, bool rest) {
+    constexpr uint32_t NPS = LOOK + 2;
+    const int kp = k + LOOK + 1;  // psi tile issued at trip k
+    if (psi && c.car && kp >= 0 && kp < c.NT) mbar_expect_tx(c.mbar + ((c.seq0 + (uint32_t)kp) % NPS), c.psi_tx);
+    if (rest && k + 1 >= 0 && k + 1 < c.NT) mbar_expect_tx(c.mbar + 4 + ((c.seq0 + (uint32_t)(k + 1)) & 1u), c.rest_tx);
+  }
+  template <int LOOK>
+  static __device__ __forceinline__ void issue_tiles(const TileCtx &c, int k) {
+    const int lane = threadIdx.x;  // warp 0: lane == tid
+    expect_tiles<LOOK>(c, k, lane == 0, lane == 1);
+    __syncwarp();
+    if (lane < c.n_desc) issue_desc<LOOK>(c, k, lane);
+  }
+  // Measured alternatives (B200, c2 / c3 sampler throughput against this scheme), kept out:
+  //  * the copies spread over the eight warps (lane 0 of warp w issues descriptors w, w + 8), issued after the ring
+  //    barrier, which already implies the release of the slots: +1 % / -4.5 % (they land too late for the next trip);
+  //  * the same, issued at the top of the trip after every warp waits for the release: -7 % / -26 % (a second
+  //    CTA-wide synchronisation per tile).
   // drift psi of tile k into the ring
   template <bool LEAP, int LOOK>
   static __device__ __forceinline__ void drift_tile(const TileCtx &c, int k, double eps) {
@@ -603,6 +655,9 @@ struct DevOps {
 
   // per-tile contribution of one warp to the bottom-level bins: G[bin][k] += sum_lanes gj * E[lane][k]
   template <int KP>
+  // (fp64 atomicAdd on shared memory is a compare-and-swap spin loop, SASS ATOMS.CAST.SPIN; accumulating these bins
+  //  with fire-and-forget RED.ADD.F64 in L2 instead measured 2-3 % SLOWER on c2 and c3: the fence + L2 round trip
+  //  that finish() then needs costs more than the contention it removes)
   static __device__ __forceinline__ void add_bins(int bins_o, double (&v)[KP], int bin_l) {
     double *bins = smem_d + bins_o;
     const int lane = threadIdx.x & 31;
@@ -693,12 +748,15 @@ struct DevOps {
     const double half_eps = 0.5 * eps;
     double a_lp = 0, a_ng = 0, a_qD = 0, a_qW = 0, a_dth = 0, a_kin = 0, a_g2 = 0, a_pp = 0;
     double a_ldet = 0, a_dldet = 0;
+    // zero-inflated spots contribute log(theta + (1-theta) e^{-mu}): summed as the log of a running product
+    LogProd zi_prod;
+    zi_prod.init();
     const bool merge0 = LEAP && rho_out != nullptr;
     // the non-compositional kernels have registers to spare and few tiles per evaluation: they fold the
     // eigenvalue term into the tile loop; the compositional ones (register-critical loop) leave it to finish()
     constexpr bool kEigInLoop = KT <= 2;
-    const int n_eig = kEigInLoop ? m.n_eig : 0;
-    const double *eigu = m.eigu, *eigm = m.eigm;
+    const int n_eigg = kEigInLoop ? m.n_eigg : 0;
+    const double *eigg = m.eigg, *eiggm = m.eiggm;
 
     if (c.car)
       for (int k0 = 0; k0 < LOOK && k0 < NT; ++k0) {
@@ -719,23 +777,20 @@ struct DevOps {
         e[0] = 1.0;
       }
       if (kEigInLoop && c.car) {
-        // one distinct eigenvalue of the CAR precision per thread and tile: sum_i mult_i log1m(a lambda_i)
+        // one group of eight distinct eigenvalues of the CAR precision per thread and tile (the groups fill the
+        // first tiles densely: whole warps either have one or skip the block)
         const int ei = k * kTile + tid;
-        if (ei < n_eig) {
-          const double lam = __ldg(eigu + ei), mult = __ldg(eigm + ei);
-          const double x = a_car * lam;
-          a_ldet += mult * log1p(-x);
-          a_dldet += mult * (-lam / (1.0 - x));
-        }
+        if (ei < n_eigg) eig_group_terms(eigg + (size_t)ei * kEigGroup, __ldg(eiggm + ei), a_car, a_ldet, a_dldet);
       }
-      if (c.car && k + LOOK < NT) drift_tile<LEAP, LOOK>(c, k + LOOK, eps);
+      PW(w_psi, if (c.car && k + LOOK < NT) drift_tile<LEAP, LOOK>(c, k + LOOK, eps));
       const uint32_t seq = c.seq0 + (uint32_t)k;
       if (tid < 32) {
-        // psi(k+2) and rest(k+1) go into the slots of tile k-1: wait until every thread has released them
-        if (k > 0) mbar_wait(c.mbar + 8 + ((seq - 1u) & 1u), ((seq - 1u) >> 1) & 1u);
-        issue_tiles<LOOK>(c, k);
+        // psi(k+look+1) and rest(k+1) go into the slots of tile k-1: wait until every thread has released them
+        PW(w_rel, if (k > 0) mbar_wait(c.mbar + 8 + ((seq - 1u) & 1u), ((seq - 1u) >> 1) & 1u));
+        PW(w_issue, issue_tiles<LOOK>(c, k));
       }
-      mbar_wait(c.mbar + 4 + (seq & 1u), (seq >> 1) & 1u);
+      PW(w_rest, mbar_wait(c.mbar + 4 + (seq & 1u), (seq >> 1) & 1u));
+      PWSTART();
       const double *pd = smem_d + c.psi_o + (seq % NPS) * 4 * kTile;  // q, p, g, minv of psi, tile k
       const double *rd = smem_d + c.rest_o + (seq & 1u) * (c.stage_bytes >> 3);
       const int *ri = reinterpret_cast<const int *>(rd + 5 * kTile);
@@ -782,10 +837,12 @@ struct DevOps {
           }
           // split barrier: every thread announced its part of ring(k+1) right after drifting it; only now,
           // with the independent work above already issued, do we need all of them
+          PWMARK(w_pre);
           if (k + LOOK < NT) {
             const uint32_t sl = seq + (uint32_t)LOOK;
-            mbar_wait(c.mbar + 6 + (sl & 1u), (sl >> 1) & 1u);
+            PW(w_ring, mbar_wait(c.mbar + 6 + (sl & 1u), (sl >> 1) & 1u));
           }
+          PWSTART();
           psi_j = ringp[j & RMASK];
           if (ew == 6) {
             Wpsi = ((ringp[pos[0]] + ringp[pos[1]]) + (ringp[pos[2]] + ringp[pos[3]])) + (ringp[pos[4]] + ringp[pos[5]]);
@@ -799,16 +856,22 @@ struct DevOps {
         }
         ll += sig03 * eps_j;
         const double eta = ll + rd[4 * kTile + tid];
-        const double mu = exp(eta);
+        const double mu = exp_fast(eta);
         const int y = ri[tid];
         if (c.zi && y == 0) {
           // log(theta + (1-theta) e^{-mu}) = log_sum_exp(log theta, log1m theta - mu); the two softmax
           // weights are theta / s and z / s
-          const double em = exp(-mu);
+          const double em = exp_fast(-mu);
           const double z = om_theta * em;
           const double s = theta + z;
-          const double inv_s = 1.0 / s;
-          a_lp += log(s);
+          double inv_s;
+          if (s > 1e-290) {  // always, short of theta underflowing
+            inv_s = rcp_fast(s);
+            zi_prod.mul(s);
+          } else {
+            inv_s = 1.0 / s;
+            a_lp += log(s);
+          }
           gj = -(mu * z) * inv_s;
           a_dth += (1.0 - em) * inv_s;
         } else {
@@ -862,13 +925,15 @@ struct DevOps {
           if (merge0) rho_out[c.o_psi + j] = 0.0;
         }
       }
+      PWMARK(w_post);
       mbar_arrive(c.mbar + 8 + (seq & 1u));  // this thread no longer reads the staged inputs of tile k
 #pragma unroll
       for (int i = 0; i < KP; ++i) e[i] *= gj;
-      add_bins<KP>(c.bins_o, e, bin);
+      PW(w_bins, add_bins<KP>(c.bins_o, e, bin));
     }
     tile_seq = (c.seq0 + (uint32_t)NT) % (4u * NPS);
     const long long t_fin = clock64();
+    if (c.zi) a_lp += zi_prod.log_value();
     // the zi-only part of d/dtheta was accumulated as (1 - e^{-mu}) / s; finish() expects it in a_dth
     finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out, sp, rho_out,
                  a_pp, pp_out, kEigInLoop, a_ldet, a_dldet);

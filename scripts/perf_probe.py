@@ -1,5 +1,5 @@
 """Scratch probe (GPU box): throughput of the sampler on named shapes; prints one line per shape."""
-import sys, time, json
+import os, sys, time, json
 import numpy as np
 sys.path.insert(0, ".")
 from csplotch_b200 import api, synth
@@ -32,7 +32,7 @@ def probe(name, family, shared, G, nch, iters, chunk):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c3"]
     if "c2" in which:
-        probe("c2", "splotch_stan_model", synth.shared_c2(), 148, 4, 60, 20)
+        probe("c2", "splotch_stan_model", synth.shared_c2(), int(os.environ.get("PROBE_G", "148")), 4, 60, 20)
     if "c3" in which:
         probe("c3", "comp_splotch_stan_model", synth.shared_c3(), 74, 4, 12, 4)
     if "c4" in which:

@@ -168,3 +168,47 @@ def test_pinned_buffers_give_the_same_results():
     for k in want_summ:
         assert np.array_equal(want_summ[k], got_summ[k])
     del out, got_draws, summ_buf, got_summ, counts          # frees the page-locked memory with the last view
+
+
+def test_init_file_round_trip(golden_dir, tmp_path):
+    """CmdStan `init=FILE.json` (bin/splotch_vinit:177-194): constrained values keyed by CSV column name -> theta."""
+    import json
+    for fam, path in (("comp_splotch_stan_model", os.path.join(golden_dir, "c1", "data_3.R")), ("splotch_stan_model", None)):
+        if path:
+            data = rdump.read_rdump(path)
+        else:
+            shared0 = synth.shared_tiny(seed=2, family=fam, n_levels=2, zi=0)
+            data = dict(shared0, counts=synth.simulate_counts(shared0, 1, 3)["counts"][0])
+        shared = {k: v for k, v in data.items() if k not in rdump.GENE_KEYS}
+        model = api.Model(shared, fam)
+        comp = fam.startswith("comp")
+        batch = api.Batch(model, np.asarray(data["counts"])[None], np.asarray(data["beta_prior_mean"])[None] if comp else None,
+                          np.asarray(data["beta_prior_std"])[None] if comp else None)
+        rng = np.random.default_rng(8)
+        theta = rng.normal(0, 0.7, model.dim)
+        cols, vals = model.column_names(), batch.write_array(theta[None])[0]
+        init = dict(zip(cols, vals.tolist()))           # a Pathfinder / CSV row: parameters and transformed parameters
+        init.update({"lp__": -1.0, "lp_approx__": 0.0})
+        got = api.unconstrain(model, init)
+        assert np.max(np.abs(got - theta)) < 1e-11
+        s = api.Sampler(batch, api.nuts_cfg(5, 5, 1, seed=1), theta_init=got[None, None, :])
+        assert np.max(np.abs(s.state()[0][0, 0] - theta)) < 1e-11
+        # absent parameters start uniform(-2, 2); structured (CmdStan JSON) arrays are accepted as well
+        part = {"sigma": float(init["sigma"]), "noise_raw": [init["noise_raw.%d" % (i + 1)] for i in range(model.N)]}
+        th2 = api.unconstrain(model, part, seed=3)
+        lay = {n: i for n, i, _ in api.param_layout(model)}
+        assert abs(th2[lay["sigma"]] - theta[lay["sigma"]]) < 1e-12
+        assert np.allclose(th2[[lay["noise_raw.%d" % (i + 1)] for i in range(model.N)]],
+                           theta[[lay["noise_raw.%d" % (i + 1)] for i in range(model.N)]], atol=1e-12)
+        assert np.all(np.abs(th2) <= np.maximum(2.0, np.abs(theta) + 1e-9))
+        if comp:
+            p = tmp_path / "init_3_1.json"
+            p.write_text(json.dumps(init))
+            out = str(tmp_path / "o.csv")
+            argv = ["/x/comp_splotch_stan_model", "sample", "num_samples=5", "num_warmup=5", "random", "id=1", "init=" + str(p),
+                    "data", "file=" + path, "output", "file=" + out]
+            assert cli.cmdstan_shim(argv) == 0 and len(open(out).read().splitlines()) == 6
+            bad = tmp_path / "bad.json"
+            bad.write_text(json.dumps({"tau.1": -3.0}))
+            argv[6] = "init=" + str(bad)
+            assert cli.cmdstan_shim(argv) == 1
