@@ -260,8 +260,8 @@ def main():
     # path: counts of Ge genes (page-locked host memory) -> Batch (H2D) -> Sampler -> warm-up + sampling
     # transitions from initialisation -> draws of the non-spot block + posterior summaries of every spot (D2H
     # into page-locked host arrays).  The page-locked buffers are allocated once, outside the timed region.
-    Ge = args.e2e_genes or min(G, 1184 if N < 10000 else 148)
-    e2e_iters = args.e2e_iters or (50 if N < 10000 else 8)
+    Ge = args.e2e_genes or min(G, 4736 if N < 10000 else 148)
+    e2e_iters = args.e2e_iters or (50 if N < 10000 else 24)
     e_warm, e_samp = e2e_iters // 2, e2e_iters - e2e_iters // 2
     counts_host = api.pinned_empty((Ge, N), np.int32)
     counts_host[...] = genes["counts"][:Ge]
