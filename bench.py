@@ -217,10 +217,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    t_start = time.time()
+
+    def note(msg):
+        if rank == 0:
+            print("[bench %6.1fs] %s" % (time.time() - t_start, msg), file=sys.stderr, flush=True)
+
     wl = WORKLOADS[args.workload]
     G = args.genes or wl[1]
     iters = args.iters or wl[2]
     family, shared, genes = make_inputs(args.workload, G, rank)
+    note("synthetic inputs ready (%d genes)" % G)
     model = api.Model(shared, family)
     N, D = model.N, model.dim
     B_leap, B_grad = 56 * D + 4 * N, 16 * D + 4 * N
@@ -234,6 +241,7 @@ def main():
     for _ in range(args.warmup):
         sampler.advance(iters, sync=True)
     c0 = sampler.counters()
+    note("resident arm: warm-up steps done")
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -254,6 +262,7 @@ def main():
     leaps = c1["n_leapfrog"] - c0["n_leapfrog"]
     launches = c1["n_launches"] - c0["n_launches"]
     del sampler
+    note("resident arm: %d timed steps done" % args.steps)
 
     # ---- e2e arm: host buffers through the C ABI, copies inside the timed region --------------------
     # One step = one complete small job for a gene block through the public API, the way bin/splotch uses the
@@ -284,15 +293,17 @@ def main():
         return cnt["n_grad"], counts_host.nbytes + (pm.nbytes + ps.nbytes if pm is not None else 0), d2h, cnt["n_launches"]
 
     e2e_step()
+    note("e2e arm: warm-up step done (%d genes x %d transitions)" % (Ge, e2e_iters))
     barrier()
     t0 = time.time()
     e_grads, h2d, d2h, e_launches = 0, 0, 0, 0
-    e_steps = max(2, min(args.steps, 4))
+    e_steps = 2        # each step is a complete job (c2: 18 944 chains x 50 transitions, ~40 s): two keep the default run ~3.5 min
     for _ in range(e_steps):
         g, a, b_, nl = e2e_step()
         e_grads += g; h2d = a; d2h = b_; e_launches += nl
     barrier()
     e_dt = time.time() - t0
+    note("e2e arm: %d timed steps done" % e_steps)
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
     if world > 1:
