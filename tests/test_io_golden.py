@@ -126,3 +126,31 @@ def test_cli_gene_spec():
     assert cli.parse_genes("7") == [7]
     assert cli.parse_genes("1-3,9,11-12") == [1, 2, 3, 9, 11, 12]
     assert cli.data_path("DATA", 3661).endswith(os.path.join("DATA", "36", "data_3661.R"))
+
+
+def test_param_layout_and_unconstrain_without_a_device():
+    """CmdStan `init=` files (bin/splotch_vinit:177-194): names -> positions in the unconstrained vector
+    (include/csplotch.h layout) and the constraining transforms; pure host logic, checked on a stand-in model."""
+    from types import SimpleNamespace as NS
+    from csplotch_b200 import api
+    comp = NS(levels=(1, 2, 0), N=5, C=3, K=2, car=1, zi=1, nb=1, family=1, dim=5 + 3 * 3 * 2 + 2 + 1 + 1 + 1 + 1 + 5)
+    lay = api.param_layout(comp)
+    assert sorted(i for _, i, _ in lay) == list(range(comp.dim))
+    pos = {n: i for n, i, _ in lay}
+    # psi | beta_raw[(i*C + j)*K + k] | tau a sigma sigma_level_2 theta phi | noise_raw
+    assert pos["psi.1"] == 0 and pos["beta_raw.1.1.1"] == 5 and pos["beta_raw.1.1.2"] == 6 and pos["beta_raw.2.1.1"] == 5 + 6
+    assert [pos[n] for n in ("tau.1", "a.1", "sigma", "sigma_level_2.1", "theta.1", "phi.1")] == list(range(23, 29))
+    assert pos["noise_raw.5"] == comp.dim - 1
+    plain = NS(levels=(2, 0, 0), N=4, C=3, K=1, car=0, zi=0, nb=0, family=0, dim=6 + 1 + 4)
+    pos = {n: i for n, i, _ in api.param_layout(plain)}
+    assert pos["beta_raw.2.1"] == 1 and pos["beta_raw.1.2"] == 2 and pos["sigma"] == 6     # column-major i + L*j
+    th = api.unconstrain(plain, {"sigma": 2.0, "beta_raw": [[1, 2, 3], [4, 5, 6]], "log_lambda.1": 9.0, "lp__": -3}, seed=1)
+    assert th[:6].tolist() == [1, 4, 2, 5, 3, 6] and abs(th[6] - np.log(2.0)) < 1e-15
+    assert np.all(np.abs(th[7:]) <= 2.0)                                                     # absent: uniform(-2, 2)
+    th = api.unconstrain(comp, {"a.1": 0.25, "theta": [0.5], "phi.1": 1.0 + 1e-6, "tau": 3.0})
+    pos = {n: i for n, i, _ in lay}
+    assert abs(th[pos["a.1"]] - np.log(1 / 3)) < 1e-15 and th[pos["theta.1"]] == 0.0
+    assert abs(th[pos["phi.1"]]) < 1e-9 and abs(th[pos["tau.1"]] - np.log(3.0)) < 1e-15
+    for bad in ({"tau.1": -1.0}, {"a.1": 1.0}, {"phi.1": 1e-7}):
+        with pytest.raises(api.CsplotchError):
+            api.unconstrain(comp, bad)
