@@ -11,9 +11,14 @@ Inputs are the unchanged `DATA/<g//100>/data_<g>.R` files of splotch_generate_in
 `OUT/<g//100>/combined_<g>.csv` (header + draws, chain-major, no comments) or, with -s,
 `combined_<g>.hdf5` (summary layout of summarize_stan_hdf5; .npz with the same keys without h5py).
 
+`splotch_vinit` (`main_vinit`) — same flags as /root/reference/bin/splotch_vinit:15-36: multi-path Pathfinder of every
+gene (`pathfinder.py`, densities on the GPU), NUM_CHAINS of its draws as starting points, 150 warm-up transitions
+(bin/splotch_vinit:137-194) — without the CSV -> JSON -> init= round trip.
+
 `cmdstan_shim` accepts the argv contract of the CmdStan executable itself
 (`BINARY sample num_samples=N num_warmup=N random id=CHAIN data file=IN.R output file=OUT.csv`) so that the
-unmodified reference `bin/splotch` also works with `-b <shim named like the model>`.
+unmodified reference `bin/splotch` also works with `-b <shim named like the model>`; it also accepts
+`BINARY pathfinder num_draws=M num_paths=C data file=IN.R output file=OUT.csv` (bin/splotch_vinit:140).
 """
 from __future__ import annotations
 
@@ -55,8 +60,14 @@ def load_genes(data_dir: str, gene_ids):
     return shared, genes
 
 
+VINIT_NUM_DRAWS = 1000     # NUM_INIT, bin/splotch_vinit:137
+VINIT_NUM_WARMUP = 150     # bin/splotch_vinit:194
+
+
 def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chains, summary, seed=0,
-                 num_warmup=None, device=0):
+                 num_warmup=None, device=0, vinit=None):
+    """`vinit`: None, or a dict of `pathfinder.pathfinder` options — every chain then starts at a Pathfinder draw of
+    its gene (bin/splotch_vinit:137-182) instead of uniform(-2, 2)."""
     from . import api, _lib
     api.check(_lib.lib().csplotch_set_device(device))
     model = api.Model(shared, family)
@@ -65,13 +76,24 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
                       genes.get("beta_prior_std") if fam == 1 else None, gene_id0=int(gene_ids[0]))
     nw = num_samples if num_warmup is None else num_warmup          # bin/splotch:131 num_warmup=num_samples
     cfg = api.nuts_cfg(nw, num_samples, num_chains, seed=seed, keep_draws=not summary)
-    s = api.Sampler(batch, cfg).run(chunk=50)
+    theta_init, pf_failed = None, np.zeros(len(gene_ids), dtype=bool)
+    if vinit is not None:
+        from . import pathfinder
+        opts = dict(num_paths=num_chains, num_draws=VINIT_NUM_DRAWS, num_out=num_chains, seed=seed)
+        opts.update(vinit)
+        pf = pathfinder.pathfinder(pathfinder.BatchTarget(batch), **opts)
+        pf_failed = ~np.isfinite(pf.lp).all(axis=1)
+        theta_init = pf.draws
+    s = api.Sampler(batch, cfg, theta_init=theta_init).run(chunk=50)
     status, iters = s.status()
     cols = model.column_names()
     written = []
     theta = s.theta_draws() if not summary else None
     diag, _, _ = s.draws()
     for i, g in enumerate(gene_ids):
+        if pf_failed[i]:
+            print("Error: Pathfinder run failed! (gene %d)" % g, file=sys.stderr)   # bin/splotch_vinit:140
+            continue
         if (status[i] != 0).any():
             # a failed chain: like a failed CmdStan run, no output file for this gene (error_exit, bin/splotch:131)
             print("Error: sampling failed for gene %d (status %s)" % (g, status[i].tolist()), file=sys.stderr)
@@ -90,8 +112,16 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
     return written, s
 
 
-def main(argv=None):
-    ap = argparse.ArgumentParser(prog="splotch", description="A wrapper for running Splotch (B200-native sampler)")
+def main_vinit(argv=None):
+    """`splotch_vinit`: Pathfinder-initialised chains and a 150-transition warm-up."""
+    return main(argv, vinit=True)
+
+
+def main(argv=None, vinit=False):
+    ap = argparse.ArgumentParser(prog="splotch_vinit" if vinit else "splotch",
+                                 description="A wrapper for running Splotch with Pathfinder initialization "
+                                             "(B200-native)" if vinit else
+                                             "A wrapper for running Splotch (B200-native sampler)")
     ap.add_argument("-g", required=True, help="gene index (1-based); ranges/lists allowed: 1-100,205")
     ap.add_argument("-d", required=True, help="data directory")
     ap.add_argument("-o", required=True, help="output directory")
@@ -102,6 +132,8 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--batch", type=int, default=512, help="genes resident on the GPU at once")
     ap.add_argument("--device", type=int, default=0)
+    if vinit:
+        ap.add_argument("--max-lbfgs-iters", type=int, default=1000, help="Pathfinder: L-BFGS iterations per path")
     a = ap.parse_args(argv)
     gene_ids = parse_genes(a.g)
     seed = a.seed if a.seed is not None else (int.from_bytes(os.urandom(4), "little"))   # CmdStan seeds from the clock
@@ -129,6 +161,11 @@ def main(argv=None):
         dim = (2 if int(head.get("car", 1)) else 1) * n_spots + 4096
         per_gene = a.c * 8 * (4 * dim + 6 * n_spots + (0 if a.s else a.n * dim))
         a.batch = max(1, min(a.batch, int(float(os.environ.get("CSPLOTCH_MEM_GB", "60")) * 1e9 // per_gene)))
+        if vinit:
+            # host side of Pathfinder: ~45 D-vectors per gene-path (iterate, gradient, 2 x 5 history pairs, the
+            # factors of the current and the best approximation, line-search candidates)
+            a.batch = max(1, min(a.batch, int(float(os.environ.get("CSPLOTCH_HOST_GB", "16")) * 1e9
+                                              // (a.c * 8 * dim * 45))))
     except (OSError, KeyError):
         pass  # missing first file: the per-run loader reports it
     # contiguous runs keep gene_id0 + i == gene id (the RNG stream is keyed by the gene index)
@@ -137,7 +174,11 @@ def main(argv=None):
     for run in runs:
         try:
             shared, genes = load_genes(a.d, run)
-            sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device)
+            if vinit:
+                sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device,
+                             num_warmup=VINIT_NUM_WARMUP, vinit=dict(max_lbfgs_iters=a.max_lbfgs_iters))
+            else:
+                sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device)
         except Exception as e:  # noqa: BLE001
             print("Error: Stan run failed! (%s)" % e, file=sys.stderr)
             rc = 1
@@ -149,9 +190,10 @@ def cmdstan_shim(argv=None, family=None):
     argv = list(sys.argv if argv is None else argv)
     family = family or os.path.basename(argv[0])
     args = argv[1:]
-    if not args or args[0] != "sample":
-        print("only the `sample` method is supported", file=sys.stderr)
+    if not args or args[0] not in ("sample", "pathfinder"):
+        print("only the `sample` and `pathfinder` methods are supported", file=sys.stderr)
         return 1
+    method = args[0]
     kv = {}
     section = None
     for tok in args[1:]:
@@ -171,6 +213,22 @@ def cmdstan_shim(argv=None, family=None):
     fam = api.family_from_binary(family)
     batch = api.Batch(model, np.asarray(data["counts"])[None], data.get("beta_prior_mean") if fam == 1 else None,
                       data.get("beta_prior_std") if fam == 1 else None)
+    out = kv.get("output.file", "output.csv")
+    if method == "pathfinder":
+        # bin/splotch_vinit:140; CmdStan's output: lp_approx__, lp__, path__, then the write_array columns
+        from . import pathfinder
+        opt = {k: int(kv[k]) for k in ("num_paths", "num_draws", "history_size", "num_elbo_draws", "max_lbfgs_iters")
+               if k in kv}
+        opt.setdefault("num_paths", 4)
+        opt.setdefault("num_draws", 1000)
+        pf = pathfinder.pathfinder(pathfinder.BatchTarget(batch), seed=seed, **opt)
+        if not np.isfinite(pf.lp[0]).all():
+            print("Pathfinder failed: no path produced a usable approximation", file=sys.stderr)
+            return 1
+        vals = batch.write_array(pf.draws[0], gene_of=np.zeros(pf.draws.shape[1], dtype=np.int32))
+        lead = np.stack([pf.lp_approx[0], pf.lp[0], pf.path[0].astype(np.float64)], axis=1)
+        stancsv.write_combined_csv(out, model.column_names(), lead, vals, lead_cols=stancsv.PATHFINDER_COLS)
+        return 0
     # one chain per process like CmdStan; chain ids start at 1, so run chain_id chains' worth of keying
     cfg = api.nuts_cfg(num_warmup, num_samples, 1, seed=seed + 7919 * (chain_id - 1), keep_draws=True)
     # init=FILE.json: constrained starting values (bin/splotch_vinit:194); init=R: radius of the uniform start
@@ -193,7 +251,6 @@ def cmdstan_shim(argv=None, family=None):
     diag, _, _ = s.draws()
     th = s.theta_draws()[0, 0]
     vals = batch.write_array(th, gene_of=np.zeros(len(th), dtype=np.int32))
-    out = kv.get("output.file", "output.csv")
     stancsv.write_combined_csv(out, model.column_names(), diag[0, 0], vals)
     return 0
 

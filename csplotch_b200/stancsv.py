@@ -17,16 +17,20 @@ import os
 import numpy as np
 
 SAMPLER_COLS = ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__"]
+PATHFINDER_COLS = ["lp_approx__", "lp__", "path__"]      # leading columns of `BINARY pathfinder` output
 SUMMARY_VARS = ["log_lambda", "beta_level_1", "beta_level_2", "beta_level_3", "psi", "sigma", "sigma_level_2",
                 "sigma_level_3", "theta", "tau", "a"]
 
 
-def write_combined_csv(path: str, columns, diag: np.ndarray, values: np.ndarray) -> None:
-    """diag: (S, 7) sampler columns; values: (S, n_outputs) in `columns` order; rows are chain-major."""
-    assert diag.shape[0] == values.shape[0] and values.shape[1] == len(columns)
+def write_combined_csv(path: str, columns, diag: np.ndarray, values: np.ndarray, lead_cols=None) -> None:
+    """diag: (S, 7) sampler columns; values: (S, n_outputs) in `columns` order; rows are chain-major.
+    `lead_cols`: names of the leading columns when they are not the sampler's (Pathfinder output:
+    lp_approx__, lp__, path__)."""
+    lead_cols = SAMPLER_COLS if lead_cols is None else list(lead_cols)
+    assert diag.shape[0] == values.shape[0] and values.shape[1] == len(columns) and diag.shape[1] == len(lead_cols)
     tmp = path + ".tmp"
     with open(tmp, "w") as f:
-        f.write(",".join(SAMPLER_COLS + list(columns)) + "\n")
+        f.write(",".join(lead_cols + list(columns)) + "\n")
         full = np.concatenate([diag, values], axis=1)
         for row in full:
             f.write(",".join(_fmt(v) for v in row) + "\n")

@@ -1,0 +1,172 @@
+"""Control flow of `splotch_vinit` and of the shim's `pathfinder` method without a device: `api.Model / Batch / Sampler`
+are replaced by stand-ins that answer from the CPU oracle (tests only — the product has no such path), so that the
+host logic between the reference's files and the C ABI is exercised here: /root/reference/bin/splotch_vinit:137-194."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from csplotch_b200 import api, cli, rdump, stancsv
+
+
+class _Model:
+    def __init__(self, data, family):
+        self.family = api.family_from_binary(family)
+        self._shared, self._fam_name = dict(data), os.path.basename(str(family))
+        d = dict(data, counts=np.zeros(int(np.sum(data["N_spots"])), dtype=np.int32))
+        if self.family == 1:
+            K = int(d["N_celltypes"])
+            d.update(beta_prior_mean=np.zeros(K), beta_prior_std=np.ones(K))
+        o = oracle.Oracle(d, self.family)
+        self.N, self.dim, self.K, self.n_outputs = o.N, o.dim, o.K, o.n_out
+        self.C = int(d["N_covariates"])
+        self.levels = (int(d["N_level_1"]), int(d.get("N_level_2", 0)), int(d.get("N_level_3", 0)))
+        self.car, self.zi = int(d.get("car", 0)), int(d.get("zi", 0))
+        self.nb = int(d.get("nb", 0)) if self.family == 1 else 0
+
+    column_names = api.Model.column_names
+
+
+class _Batch:
+    def __init__(self, model, counts, beta_prior_mean=None, beta_prior_std=None, gene_id0=0):
+        self.model, self.gene_id0 = model, gene_id0
+        counts = np.asarray(counts).reshape(-1, model.N)
+        self.G = len(counts)
+        self.o = []
+        for g in range(self.G):
+            d = dict(model._shared, counts=counts[g])
+            if model.family == 1:
+                d.update(beta_prior_mean=np.asarray(beta_prior_mean).reshape(self.G, -1)[g],
+                         beta_prior_std=np.asarray(beta_prior_std).reshape(self.G, -1)[g])
+            self.o.append(oracle.Oracle(d, model.family))
+
+    def log_prob_grad(self, theta, gene_of=None, jacobian=True, want_grad=True):
+        theta = np.asarray(theta).reshape(-1, self.model.dim)
+        go = np.zeros(len(theta), dtype=int) if gene_of is None else np.asarray(gene_of)
+        out = [self.o[go[i]].log_prob_grad(theta[i], jacobian=jacobian) for i in range(len(theta))]
+        lp = np.array([a for a, _ in out])
+        return (lp, np.stack([b for _, b in out])) if want_grad else lp
+
+    def write_array(self, theta, gene_of=None):
+        theta = np.asarray(theta).reshape(-1, self.model.dim)
+        go = np.zeros(len(theta), dtype=int) if gene_of is None else np.asarray(gene_of)
+        return np.stack([self.o[go[i]].write_array(theta[i]) for i in range(len(theta))])
+
+
+class _Sampler:
+    started = []          # (num_warmup, theta_init) of every sampler made, for the assertions
+
+    def __init__(self, batch, cfg, theta_init=None):
+        self.batch, self.cfg, self.model = batch, cfg, batch.model
+        self.G, self.nch = batch.G, cfg.num_chains
+        self.theta_init = None if theta_init is None else np.asarray(theta_init).reshape(self.G, self.nch, -1)
+        _Sampler.started.append((cfg.num_warmup, self.theta_init))
+
+    def run(self, chunk=None):
+        ocfg = oracle.nuts_cfg(self.cfg.num_warmup, self.cfg.num_samples, seed=int(self.cfg.seed))
+        D = self.model.dim
+        self._diag = np.zeros((self.G, self.nch, self.cfg.num_samples, 7))
+        self._theta = np.zeros((self.G, self.nch, self.cfg.num_samples, D))
+        self._status = np.zeros((self.G, self.nch), dtype=np.int32)
+        for g in range(self.G):
+            for c in range(self.nch):
+                qi = None if self.theta_init is None else self.theta_init[g, c]
+                out = self.batch.o[g].nuts(ocfg, gene_id=self.batch.gene_id0 + g, chain_id=c + 1, q_init=qi)
+                self._status[g, c] = out["status"]
+                self._diag[g, c], self._theta[g, c] = out["draws"][:, :7], out["draws"][:, 7:]
+        return self
+
+    def status(self):
+        return self._status, np.full((self.G, self.nch), self.cfg.num_warmup + self.cfg.num_samples)
+
+    def draws(self, out=None):
+        return self._diag, None, None
+
+    def theta_draws(self):
+        return self._theta
+
+
+@pytest.fixture()
+def host_only(monkeypatch):
+    monkeypatch.setattr(api, "Model", _Model)
+    monkeypatch.setattr(api, "Batch", _Batch)
+    monkeypatch.setattr(api, "Sampler", _Sampler)
+    monkeypatch.setattr(api, "check", lambda rc: None)          # csplotch_set_device needs a device
+    _Sampler.started = []
+    return _Sampler
+
+
+def _c1_data_dir(golden_dir, tmp_path, genes):
+    d = tmp_path / "data" / "0"
+    d.mkdir(parents=True)
+    for g in genes:
+        (d / ("data_%d.R" % g)).write_text(open(os.path.join(golden_dir, "c1", "data_%d.R" % g)).read())
+    return str(tmp_path / "data")
+
+
+def test_splotch_vinit_control_flow(host_only, golden_dir, tmp_path):
+    data_dir = _c1_data_dir(golden_dir, tmp_path, (2, 3))
+    out = str(tmp_path / "out")
+    argv = ["-g", "2-3", "-d", data_dir, "-o", out, "-b", "/opt/bin/comp_splotch_stan_model", "-n", "12", "-c", "2",
+            "--seed", "4", "--max-lbfgs-iters", "40"]
+    assert cli.main_vinit(argv) == 0
+    (nw, init), = host_only.started
+    assert nw == 150 and init.shape == (2, 2, 94)                              # bin/splotch_vinit:194 num_warmup=150
+    # the chains start at Pathfinder draws: far better than uniform(-2, 2) starts
+    b = _Batch(_Model({k: v for k, v in rdump.read_rdump(cli.data_path(data_dir, 2)).items()
+                       if k not in rdump.GENE_KEYS}, "comp_splotch_stan_model"),
+               *[np.stack([rdump.read_rdump(cli.data_path(data_dir, g))[k] for g in (2, 3)])
+                 for k in ("counts", "beta_prior_mean", "beta_prior_std")])
+    rng = np.random.default_rng(0)
+    for g in range(2):
+        lp0 = b.log_prob_grad(init[g], gene_of=[g, g], want_grad=False)
+        rand = b.log_prob_grad(rng.uniform(-2, 2, (40, 94)), gene_of=[g] * 40, want_grad=False)
+        assert lp0.min() > np.median(rand) and np.isfinite(lp0).all()
+    for g in (2, 3):
+        lines = open(os.path.join(out, "0", "combined_%d.csv" % g)).read().splitlines()
+        assert lines[0].startswith("lp__,accept_stat__,stepsize__") and len(lines) == 1 + 2 * 12
+    # plain `splotch` keeps num_warmup = num_samples and random starts (bin/splotch:131)
+    assert cli.main(argv[:-2]) == 0
+    assert host_only.started[-1][0] == 12 and host_only.started[-1][1] is None
+
+
+def test_shim_pathfinder_then_reference_extraction_then_sample(host_only, golden_dir, tmp_path):
+    path = os.path.join(golden_dir, "c1", "data_1.R")
+    pf_csv = str(tmp_path / "output_1.csv")
+    argv = ["/x/comp_splotch_stan_model", "pathfinder", "num_draws=30", "num_paths=2", "max_lbfgs_iters=40",
+            "data", "file=" + path, "output", "file=" + pf_csv]
+    assert cli.cmdstan_shim(argv) == 0
+    # --- the reference's extraction of NUM_CHAINS random draws (bin/splotch_vinit:146-182), restated
+    first_line, draw_lines, line_count = None, [], 0
+    draws = np.random.default_rng(3).choice(30, size=2, replace=False)
+    with open(pf_csv) as fh:
+        for line in fh:
+            if not line.startswith("#"):
+                if first_line is None:
+                    first_line = line
+                else:
+                    if line_count in draws:
+                        draw_lines.append(line)
+                    line_count += 1
+    assert line_count == 30 and len(draw_lines) == 2
+    header = first_line.split(",")
+    assert header[:3] == stancsv.PATHFINDER_COLS
+    for i, last_line in enumerate(draw_lines):
+        init = {k: float(v) for k, v in zip(header, last_line.split(",")) if k not in ["lp_approx__", "lp__", "path__"]}
+        p = str(tmp_path / ("init_1_%d.json" % (i + 1)))
+        json.dump(init, open(p, "w"), indent=2)
+        out = str(tmp_path / ("output_1_%d.csv" % (i + 1)))
+        argv = ["/x/comp_splotch_stan_model", "sample", "num_samples=8", "num_warmup=150", "random", "id=%d" % (i + 1),
+                "init=" + p, "data", "file=" + path, "output", "file=" + out, "refresh=10"]
+        assert cli.cmdstan_shim(argv) == 0
+        nw, th0 = host_only.started[-1]
+        assert nw == 150 and th0.shape == (1, 1, 94)
+        # the starting point is the Pathfinder draw of that CSV line (constrained -> unconstrained round trip)
+        vals = np.array([float(v) for v in last_line.split(",")[3:]])
+        o = oracle.Oracle(rdump.read_rdump(path), "comp_splotch_stan_model")
+        assert np.abs(o.write_array(th0[0, 0]) - vals).max() < 1e-9 * max(1.0, np.abs(vals).max())
+        assert len(open(out).read().splitlines()) == 9
+    # a method the executable does not have
+    assert cli.cmdstan_shim(["/x/comp_splotch_stan_model", "optimize", "data", "file=" + path]) == 1
