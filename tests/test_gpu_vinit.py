@@ -64,8 +64,8 @@ def test_splotch_vinit_cli(golden_dir, tmp_path):
         post = stancsv.read_stan_csv(os.path.join(out, "0", "combined_%d.csv" % g), ["lp__", "beta_level_1", "sigma"])
         assert np.isfinite(post["lp__"]).all() and post["beta_level_1"].shape == (60, 1, 14, 5)
     assert cli.main_vinit(argv[:5] + [str(tmp_path / "sum"), "-s"] + argv[6:]) == 0
-    assert os.path.exists(os.path.join(str(tmp_path / "sum"), "0", "combined_2.hdf5")) or \
-        os.path.exists(os.path.join(str(tmp_path / "sum"), "0", "combined_2.npz"))
+    got = stancsv.read_summary(os.path.join(str(tmp_path / "sum"), "0", "combined_2.hdf5"))
+    assert got["beta_level_1"]["samples"].shape == (60, 1, 14, 5) and got["lambda"]["mean"].shape == (10,)
 
 
 def test_shim_pathfinder_method_and_reference_hand_over(golden_dir, tmp_path):
