@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "csplotch.cu")
 HOST_SRC = os.path.join(HERE, "csrc", "ingest.cpp")   # host-only part of the ABI (R-dump fast path)
-DEPS = [SRC, HOST_SRC] + [os.path.join(HERE, "csrc", f) for f in ("device_ops.cuh", "nuts_core.h", "philox.h")] + [
+DEPS = [SRC, HOST_SRC] + [os.path.join(HERE, "csrc", f) for f in ("device_ops.cuh", "nuts_core.h", "philox.h", "fastmath.h")] + [
     os.path.join(ROOT, "include", "csplotch.h")]
 OUT = os.path.join(HERE, "libcsplotch_b200.so")
 
