@@ -53,6 +53,7 @@ SYMBOLS = [
     "csplotch_sampler_advance", "csplotch_sampler_sync", "csplotch_sampler_last_ms", "csplotch_sampler_counters",
     "csplotch_sampler_status", "csplotch_sampler_profile", "csplotch_sampler_get_draws", "csplotch_sampler_get_theta_draws",
     "csplotch_sampler_get_state", "csplotch_sampler_get_spot_summaries", "csplotch_rdump_read_genes", "csplotch_host_alloc", "csplotch_host_free",
+    "csplotch_csv_write",
 ]
 
 _lib = None

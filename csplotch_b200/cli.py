@@ -65,7 +65,7 @@ VINIT_NUM_WARMUP = 150     # bin/splotch_vinit:194
 
 
 def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chains, summary, seed=0,
-                 num_warmup=None, device=0, vinit=None):
+                 num_warmup=None, device=0, vinit=None, sig_figs=0):
     """`vinit`: None, or a dict of `pathfinder.pathfinder` options — every chain then starts at a Pathfinder draw of
     its gene (bin/splotch_vinit:137-182) instead of uniform(-2, 2)."""
     from . import api, _lib
@@ -90,6 +90,7 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
     written = []
     theta = s.theta_draws() if not summary else None
     diag, _, _ = s.draws()
+    good = []
     for i, g in enumerate(gene_ids):
         if pf_failed[i]:
             print("Error: Pathfinder run failed! (gene %d)" % g, file=sys.stderr)   # bin/splotch_vinit:140
@@ -98,17 +99,25 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
             # a failed chain: like a failed CmdStan run, no output file for this gene (error_exit, bin/splotch:131)
             print("Error: sampling failed for gene %d (status %s)" % (g, status[i].tolist()), file=sys.stderr)
             continue
-        d = os.path.join(out_dir, str(g // 100))
-        os.makedirs(d, exist_ok=True)
-        if summary:
-            written.append(stancsv.write_summary(os.path.join(d, "combined_%d.hdf5" % g),
+        os.makedirs(os.path.join(out_dir, str(g // 100)), exist_ok=True)
+        good.append(i)
+    if summary:
+        for i in good:
+            g = gene_ids[i]
+            written.append(stancsv.write_summary(os.path.join(out_dir, str(g // 100), "combined_%d.hdf5" % g),
                                                  stancsv.summary_from_sampler(s, i)))
-        else:
-            th = theta[i].reshape(-1, model.dim)
-            vals = batch.write_array(th, gene_of=np.full(len(th), i, dtype=np.int32))
-            p = os.path.join(d, "combined_%d.csv" % g)
-            stancsv.write_combined_csv(p, cols, diag[i].reshape(-1, 7), vals)
-            written.append(p)
+    else:
+        # write_array on the device and the native CSV writer, a block of genes at a time (<= 1 GB of rows on the host)
+        rows = num_chains * num_samples
+        step = max(1, min(os.cpu_count() or 1, (1 << 30) // max(1, 8 * rows * model.n_outputs)))
+        for a0 in range(0, len(good), step):
+            blk = good[a0:a0 + step]
+            th = theta[blk].reshape(-1, model.dim)
+            vals = batch.write_array(th, gene_of=np.repeat(np.asarray(blk, dtype=np.int32), rows))
+            paths = [os.path.join(out_dir, str(gene_ids[i] // 100), "combined_%d.csv" % gene_ids[i]) for i in blk]
+            stancsv.write_combined_csvs(paths, cols, diag[blk].reshape(len(blk), rows, 7),
+                                        vals.reshape(len(blk), rows, -1), sig_figs=sig_figs)
+            written += paths
     return written, s
 
 
@@ -132,6 +141,8 @@ def main(argv=None, vinit=False):
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--batch", type=int, default=512, help="genes resident on the GPU at once")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--sig-figs", type=int, default=0,
+                    help="significant digits in the CSV (CmdStan's sig_figs; 0 = shortest text that round-trips)")
     if vinit:
         ap.add_argument("--max-lbfgs-iters", type=int, default=1000, help="Pathfinder: L-BFGS iterations per path")
     a = ap.parse_args(argv)
@@ -176,9 +187,11 @@ def main(argv=None, vinit=False):
             shared, genes = load_genes(a.d, run)
             if vinit:
                 sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device,
-                             num_warmup=VINIT_NUM_WARMUP, vinit=dict(max_lbfgs_iters=a.max_lbfgs_iters))
+                             num_warmup=VINIT_NUM_WARMUP, vinit=dict(max_lbfgs_iters=a.max_lbfgs_iters),
+                             sig_figs=a.sig_figs)
             else:
-                sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device)
+                sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device,
+                             sig_figs=a.sig_figs)
         except Exception as e:  # noqa: BLE001
             print("Error: Stan run failed! (%s)" % e, file=sys.stderr)
             rc = 1
@@ -214,6 +227,7 @@ def cmdstan_shim(argv=None, family=None):
     batch = api.Batch(model, np.asarray(data["counts"])[None], data.get("beta_prior_mean") if fam == 1 else None,
                       data.get("beta_prior_std") if fam == 1 else None)
     out = kv.get("output.file", "output.csv")
+    sig_figs = max(0, int(kv.get("sig_figs", 0)))       # CmdStan: output sig_figs=N (-1 = its default)
     if method == "pathfinder":
         # bin/splotch_vinit:140; CmdStan's output: lp_approx__, lp__, path__, then the write_array columns
         from . import pathfinder
@@ -227,7 +241,8 @@ def cmdstan_shim(argv=None, family=None):
             return 1
         vals = batch.write_array(pf.draws[0], gene_of=np.zeros(pf.draws.shape[1], dtype=np.int32))
         lead = np.stack([pf.lp_approx[0], pf.lp[0], pf.path[0].astype(np.float64)], axis=1)
-        stancsv.write_combined_csv(out, model.column_names(), lead, vals, lead_cols=stancsv.PATHFINDER_COLS)
+        stancsv.write_combined_csv(out, model.column_names(), lead, vals, lead_cols=stancsv.PATHFINDER_COLS,
+                                   sig_figs=sig_figs)
         return 0
     # one chain per process like CmdStan; chain ids start at 1, so run chain_id chains' worth of keying
     cfg = api.nuts_cfg(num_warmup, num_samples, 1, seed=seed + 7919 * (chain_id - 1), keep_draws=True)
@@ -251,7 +266,7 @@ def cmdstan_shim(argv=None, family=None):
     diag, _, _ = s.draws()
     th = s.theta_draws()[0, 0]
     vals = batch.write_array(th, gene_of=np.zeros(len(th), dtype=np.int32))
-    stancsv.write_combined_csv(out, model.column_names(), diag[0, 0], vals)
+    stancsv.write_combined_csv(out, model.column_names(), diag[0, 0], vals, sig_figs=sig_figs)
     return 0
 
 

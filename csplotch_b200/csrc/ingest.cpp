@@ -252,3 +252,118 @@ extern "C" int32_t csplotch_rdump_read_genes(const char *const *paths, int32_t G
   if (!J.err.empty()) return csplotch_internal_fail(CSPLOTCH_E_INVALID, J.err.c_str());
   return CSPLOTCH_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Output fast path: `combined_<g>.csv` of many genes, in parallel, natively.
+//
+// What CmdStan's CSV writer plus the wrapper's grep / sed concatenation leave behind
+// (/root/reference/bin/splotch:131,138-140): ONE header line (the one containing `lp__`), then one row per draw,
+// chains one after the other, no `#` comment lines.  A row is 7 sampler columns + every write_array column
+// (c2: 7.9 k numbers, c3: 3.6e5) and a gene has NUM_CHAINS x NUM_SAMPLES rows, so formatting dominates the CSV mode;
+// a pool of host threads formats one file each.  Numbers: integral values print without a decimal point
+// ("3", like treedepth__ / n_leapfrog__ / divergent__ in CmdStan's files); everything else in the shortest form
+// that reads back to the same double (sig_figs = 0) or with `sig_figs` significant digits (CmdStan's `sig_figs=`,
+// whose default is 6).  Each file is written to `<path>.tmp` and renamed.  Host code only.
+#include <charconv>
+#include <cstdio>
+
+namespace {
+
+struct CsvJob {
+  const char *const *paths;
+  int32_t n_files;
+  const char *header;
+  const double *lead, *values;
+  int32_t n_lead, n_values, sig_figs;
+  int64_t n_rows;
+  std::atomic<int32_t> next{0};
+  std::mutex mu;
+  std::string err;
+};
+
+inline char *put_number(char *p, char *end, double v, int sig_figs) {
+  if (v == std::floor(v) && std::fabs(v) < 1e15) {
+    auto r = std::to_chars(p, end, (long long)v);
+    return r.ptr;
+  }
+  auto r = sig_figs > 0 ? std::to_chars(p, end, v, std::chars_format::general, sig_figs) : std::to_chars(p, end, v);
+  return r.ptr;
+}
+
+bool write_one(CsvJob &J, int32_t f, std::string &err) {
+  const std::string path = J.paths[f];
+  const std::string tmp = path + ".tmp";
+  FILE *fp = fopen(tmp.c_str(), "wb");
+  if (!fp) {
+    err = tmp + ": " + strerror(errno);
+    return false;
+  }
+  const size_t ncol = (size_t)J.n_lead + (size_t)J.n_values;
+  std::vector<char> line(ncol * 32 + 16);  // a double needs at most 24 characters
+  bool ok = fputs(J.header, fp) >= 0 && fputc('\n', fp) != EOF;
+  for (int64_t r = 0; ok && r < J.n_rows; ++r) {
+    char *p = line.data(), *end = line.data() + line.size();
+    const double *a = J.lead + ((size_t)f * J.n_rows + r) * J.n_lead;
+    const double *b = J.values + ((size_t)f * J.n_rows + r) * J.n_values;
+    for (int32_t c = 0; c < J.n_lead; ++c) {
+      p = put_number(p, end, a[c], J.sig_figs);
+      *p++ = ',';
+    }
+    for (int32_t c = 0; c < J.n_values; ++c) {
+      p = put_number(p, end, b[c], J.sig_figs);
+      *p++ = ',';
+    }
+    p[-1] = '\n';
+    ok = fwrite(line.data(), 1, (size_t)(p - line.data()), fp) == (size_t)(p - line.data());
+  }
+  if (fclose(fp) != 0) ok = false;
+  if (ok && rename(tmp.c_str(), path.c_str()) != 0) ok = false;
+  if (!ok) {
+    err = path + ": " + strerror(errno);
+    remove(tmp.c_str());
+  }
+  return ok;
+}
+
+void csv_worker(CsvJob *J) {
+  for (;;) {
+    const int32_t f = J->next.fetch_add(1);
+    if (f >= J->n_files) return;
+    std::string err;
+    if (!write_one(*J, f, err)) {
+      std::lock_guard<std::mutex> lk(J->mu);
+      if (J->err.empty()) J->err = err;
+      J->next.store(J->n_files);
+      return;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int32_t csplotch_csv_write(const char *const *paths, int32_t n_files, const char *header,
+                                      const double *lead, int32_t n_lead, const double *values, int32_t n_values,
+                                      int64_t n_rows, int32_t sig_figs, int32_t n_threads) {
+  if (n_files < 0 || n_rows < 0 || n_lead < 0 || n_values < 0 || n_lead + (int64_t)n_values < 1 || sig_figs < 0 ||
+      sig_figs > 18 || !header || (n_files > 0 && (!paths || (n_rows > 0 && ((n_lead && !lead) || (n_values && !values))))))
+    return csplotch_internal_fail(CSPLOTCH_E_INVALID, "csplotch_csv_write: bad arguments");
+  CsvJob J;
+  J.paths = paths;
+  J.n_files = n_files;
+  J.header = header;
+  J.lead = lead;
+  J.values = values;
+  J.n_lead = n_lead;
+  J.n_values = n_values;
+  J.sig_figs = sig_figs;
+  J.n_rows = n_rows;
+  int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > n_files) nt = n_files > 0 ? n_files : 1;
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(csv_worker, &J);
+  csv_worker(&J);
+  for (auto &t : pool) t.join();
+  if (!J.err.empty()) return csplotch_internal_fail(CSPLOTCH_E_INVALID, J.err.c_str());
+  return CSPLOTCH_OK;
+}

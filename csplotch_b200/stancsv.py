@@ -22,27 +22,33 @@ SUMMARY_VARS = ["log_lambda", "beta_level_1", "beta_level_2", "beta_level_3", "p
                 "sigma_level_3", "theta", "tau", "a"]
 
 
-def write_combined_csv(path: str, columns, diag: np.ndarray, values: np.ndarray, lead_cols=None) -> None:
-    """diag: (S, 7) sampler columns; values: (S, n_outputs) in `columns` order; rows are chain-major.
-    `lead_cols`: names of the leading columns when they are not the sampler's (Pathfinder output:
-    lp_approx__, lp__, path__)."""
+def write_combined_csvs(paths, columns, diag: np.ndarray, values: np.ndarray, lead_cols=None, sig_figs: int = 0,
+                        n_threads: int = 0) -> None:
+    """`combined_<g>.csv` of several genes at once through the library's native writer (`csplotch_csv_write`, host
+    threads, one file each).  diag: (F, S, 7) sampler columns; values: (F, S, n_outputs) in `columns` order; rows
+    are chain-major.  `lead_cols`: names of the leading columns when they are not the sampler's (Pathfinder output:
+    lp_approx__, lp__, path__).  CmdStan writes 6 significant digits by default (sig_figs=-1); the default here
+    (sig_figs=0) is the shortest text that reads back to the same double, so that a summary made from the CSV equals
+    the on-device summary; integral values print without a decimal point."""
+    import ctypes as C
+    from . import _lib
     lead_cols = SAMPLER_COLS if lead_cols is None else list(lead_cols)
-    assert diag.shape[0] == values.shape[0] and values.shape[1] == len(columns) and diag.shape[1] == len(lead_cols)
-    tmp = path + ".tmp"
-    with open(tmp, "w") as f:
-        f.write(",".join(lead_cols + list(columns)) + "\n")
-        full = np.concatenate([diag, values], axis=1)
-        for row in full:
-            f.write(",".join(_fmt(v) for v in row) + "\n")
-    os.replace(tmp, path)
+    paths = [os.fspath(p) for p in paths]
+    F = len(paths)
+    diag = np.ascontiguousarray(diag, dtype=np.float64).reshape(F, -1, len(lead_cols))
+    values = np.ascontiguousarray(values, dtype=np.float64).reshape(F, diag.shape[1], len(columns))
+    header = ",".join(lead_cols + list(columns)).encode()
+    arr = (C.c_char_p * F)(*[p.encode() for p in paths])
+    _lib.check(_lib.lib().csplotch_csv_write(arr, C.c_int32(F), header, diag.ctypes.data_as(C.c_void_p),
+                                             C.c_int32(diag.shape[2]), values.ctypes.data_as(C.c_void_p),
+                                             C.c_int32(values.shape[2]), C.c_int64(diag.shape[1]),
+                                             C.c_int32(sig_figs), C.c_int32(n_threads)))
 
 
-def _fmt(v: float) -> str:
-    # CmdStan writes 6 significant digits by default (sig_figs=-1); full precision is kept here so that a
-    # summary made from the CSV equals the on-device summary; integers print without a decimal point
-    if v == int(v) and abs(v) < 1e15:
-        return str(int(v))
-    return repr(float(v))
+def write_combined_csv(path: str, columns, diag: np.ndarray, values: np.ndarray, lead_cols=None, sig_figs: int = 0) -> None:
+    """One file: diag (S, 7), values (S, n_outputs)."""
+    assert np.shape(diag)[0] == np.shape(values)[0] and np.shape(values)[1] == len(columns)
+    write_combined_csvs([path], columns, np.asarray(diag)[None], np.asarray(values)[None], lead_cols, sig_figs)
 
 
 def read_stan_csv(filename: str, variables):

@@ -208,6 +208,19 @@ int32_t csplotch_sampler_get_spot_summaries(csplotch_sampler *s, double *log_lam
 int32_t csplotch_rdump_read_genes(const char *const *paths, int32_t G, int32_t N, int32_t K, int32_t *counts,
                                   double *beta_prior_mean, double *beta_prior_std, int32_t n_threads);
 
+/* ---- output fast path (host only) ------------------------------------------------------
+ * Stands in for CmdStan's CSV writer and the wrapper's concatenation of the chain files
+ * (/root/reference/bin/splotch:131,138-140): file f = `header` + '\n', then n_rows rows, each the n_lead numbers
+ * lead[f][r][:] (the sampler columns lp__ … energy__, or lp_approx__, lp__, path__ of the pathfinder method)
+ * followed by the n_values numbers values[f][r][:] (csplotch_write_array), comma separated, no `#` lines — what
+ * read_stan_csv (/root/reference/splotch/utils.py:139-232) parses.  Integral values print without a decimal point;
+ * others in the shortest form that reads back to the same double (sig_figs = 0) or with sig_figs significant digits
+ * (CmdStan's `sig_figs=`; its default is 6).  n_threads files at a time (0 = all host cores); each file is written
+ * to `<path>.tmp` and renamed.  Fails (CSPLOTCH_E_INVALID, message names the file) when a file cannot be written. */
+int32_t csplotch_csv_write(const char *const *paths, int32_t n_files, const char *header, const double *lead,
+                           int32_t n_lead, const double *values, int32_t n_values, int64_t n_rows, int32_t sig_figs,
+                           int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

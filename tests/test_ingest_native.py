@@ -97,3 +97,52 @@ def test_errors_name_the_file(tmp_path):
     with pytest.raises(CsplotchError, match="not found"):
         rdump.read_genes_native([str(nokey)], 3)
     assert rdump.read_genes_native([], N)["counts"].shape == (0, N)
+
+
+# ------------------------------------------------------------------------------------------ native CSV writer
+def test_native_csv_writer_round_trips_every_double(tmp_path):
+    """`csplotch_csv_write` (bin/splotch:131,138-140 stand-in): what read_stan_csv's float() reads back is the
+    double that was written, bit for bit; integral values have no decimal point; many files in one call."""
+    from csplotch_b200 import stancsv
+    rng = np.random.default_rng(0)
+    F, S, n = 5, 40, 300
+    cols = ["psi.%d" % (i + 1) for i in range(n - 1)] + ["sigma"]
+    diag = np.abs(rng.normal(size=(F, S, 7)))
+    diag[..., 3:6] = rng.integers(0, 1023, (F, S, 3))
+    vals = rng.normal(size=(F, S, n)) * 10.0 ** rng.integers(-300, 300, (F, S, n))
+    vals[0, 0, :8] = [0.0, -0.0, 5e-324, 1.7976931348623157e308, 1e15, 123456789012345678.0, 0.1, -2.5]
+    vals[1, 1, :3] = [np.nan, np.inf, -np.inf]
+    paths = [str(tmp_path / ("combined_%d.csv" % f)) for f in range(F)]
+    stancsv.write_combined_csvs(paths, cols, diag, vals, n_threads=3)
+    for f in range(F):
+        lines = open(paths[f]).read().split("\n")
+        assert lines[-1] == "" and len(lines) == S + 2 and not any(l.startswith("#") for l in lines)
+        assert lines[0] == ",".join(stancsv.SAMPLER_COLS + cols)
+        got = np.array([[float(t) for t in l.split(",")] for l in lines[1:-1]])
+        want = np.concatenate([diag[f], vals[f]], axis=1)
+        assert np.array_equal(got, want, equal_nan=True)                      # exact: shortest round-trip text
+        toks = lines[1].split(",")
+        assert all("." not in t and "e" not in t for t in toks[3:6])           # treedepth__, n_leapfrog__, divergent__
+        post = stancsv.read_stan_csv(paths[f], ["psi", "sigma", "lp__"])
+        assert np.array_equal(post["sigma"][:, 0], vals[f, :, -1], equal_nan=True)
+    assert open(paths[0]).read().split("\n")[1].split(",")[7:15] == [
+        "0", "0", "5e-324", "1.7976931348623157e+308", "1e+15", "123456789012345680", "0.1", "-2.5"]
+    assert not any(p.endswith(".tmp") for p in os.listdir(tmp_path))
+
+
+def test_native_csv_writer_sig_figs_and_errors(tmp_path):
+    from csplotch_b200 import stancsv
+    from csplotch_b200._lib import CsplotchError
+    vals = np.array([[[np.pi * 1e5, -np.e * 1e-7, 2.0, 1234567.0]]])
+    lead = np.array([[[-1234.56789, 1.0, 3.0]]])
+    p = str(tmp_path / "pf.csv")
+    stancsv.write_combined_csvs([p], ["a", "b", "c", "d"], lead, vals, lead_cols=stancsv.PATHFINDER_COLS, sig_figs=6)
+    hdr, row = open(p).read().splitlines()
+    assert hdr == "lp_approx__,lp__,path__,a,b,c,d"
+    assert row == "-1234.57,1,3,314159,-2.71828e-07,2,1234567"          # CmdStan's default precision
+    with pytest.raises(CsplotchError, match="no_such_dir"):
+        stancsv.write_combined_csvs([str(tmp_path / "no_such_dir" / "x.csv")], ["a", "b", "c", "d"], lead, vals,
+                                    lead_cols=stancsv.PATHFINDER_COLS)
+    # zero rows: header only (a chain file of a run with num_samples=0)
+    stancsv.write_combined_csvs([p], ["a"], np.zeros((1, 0, 7)), np.zeros((1, 0, 1)))
+    assert open(p).read() == ",".join(stancsv.SAMPLER_COLS + ["a"]) + "\n"
