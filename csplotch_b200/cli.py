@@ -219,7 +219,14 @@ def cmdstan_shim(argv=None, family=None):
     num_warmup = int(kv.get("num_warmup", 1000))
     chain_id = int(kv.get("random.id", kv.get("id", 1)))
     seed = int(kv.get("random.seed", kv.get("seed", int.from_bytes(os.urandom(4), "little"))))
-    data = rdump.read_rdump(kv["data.file"])
+    if "data.file" not in kv:
+        print("%s: `data file=<data_<g>.R>` is required" % method, file=sys.stderr)
+        return 1
+    try:
+        data = rdump.read_rdump(kv["data.file"])
+    except OSError as e:
+        print("Error reading data file %s: %s" % (kv["data.file"], e), file=sys.stderr)
+        return 1
     from . import api
     shared = {k: v for k, v in data.items() if k not in rdump.GENE_KEYS}
     model = api.Model(shared, family)

@@ -102,7 +102,9 @@ def test_cmdstan_argv_shim(golden_dir, tmp_path):
     assert lines[0].startswith("lp__,") and len(lines) == 26
     post = stancsv.read_stan_csv(out, ["beta_level_1", "log_lambda", "tau", "a", "theta"])
     assert post["beta_level_1"].shape == (25, 1, 14, 5) and np.all(post["tau"] > 0) and np.all(post["a"] < 1)
-    assert cli.cmdstan_shim(["/opt/bin/comp_splotch_stan_model", "pathfinder"]) == 1
+    assert cli.cmdstan_shim(["/opt/bin/comp_splotch_stan_model", "optimize"]) == 1       # a method this path does not have
+    assert cli.cmdstan_shim(["/opt/bin/comp_splotch_stan_model", "pathfinder"]) == 1     # no data file
+    assert cli.cmdstan_shim(["/opt/bin/comp_splotch_stan_model", "sample", "data", "file=/no/such/data_1.R"]) == 1
 
 
 def test_error_behaviour(golden_dir):
