@@ -96,14 +96,14 @@ class _Approx:
                 continue
             Sg, Yg = S[rows, :mm], Y[rows, :mm]                       # (n, mm, D)
             al = alpha[rows][:, None, :]
-            E = np.triu(np.einsum("nid,njd->nij", Sg, Yg))            # S'Y, upper triangle
+            E = np.triu(Sg @ np.swapaxes(Yg, 1, 2))                   # S'Y, upper triangle
             eta = np.einsum("nii->ni", E)
             with np.errstate(all="ignore"):
                 try:
                     Einv = np.linalg.inv(E)
                 except np.linalg.LinAlgError:
                     Einv = np.full_like(E, np.nan)
-                YaY = np.einsum("nid,njd->nij", Yg * al, Yg)
+                YaY = (Yg * al) @ np.swapaxes(Yg, 1, 2)
                 mid = YaY.copy()
                 idx = np.arange(mm)
                 mid[:, idx, idx] += eta
@@ -113,8 +113,8 @@ class _Approx:
                 G[:, mm:, mm:] = np.swapaxes(Einv, 1, 2) @ mid @ Einv
                 B = np.concatenate([Yg * al, Sg], axis=1)                 # (n, 2mm, D) = B'
                 # mean: x + Sigma grad lp = x - alpha g - B G B' g
-                Bg = np.einsum("nkd,nd->nk", B, g[rows])
-                self.mu[rows] -= np.einsum("nkd,nk->nd", B, np.einsum("nkl,nl->nk", G, Bg))
+                Bg = (B @ g[rows][:, :, None])[:, :, 0]
+                self.mu[rows] -= ((G @ Bg[:, :, None])[:, None, :, 0] @ B)[:, 0]
                 A = np.swapaxes(B / self.sqrt_alpha[rows][:, None, :], 1, 2)   # (n, D, 2mm)
                 good = np.isfinite(A).all(axis=(1, 2)) & np.isfinite(G).all(axis=(1, 2))
                 A[~good] = 0.0
@@ -139,8 +139,8 @@ class _Approx:
         """u: (n, D) shared standard normals -> phi (r, n, D), log q (r, n)."""
         phi = np.broadcast_to(u[None], (self.r,) + u.shape).copy()
         for rows, Q, T in self.groups:
-            Qu = np.einsum("rdk,nd->rnk", Q, u)
-            phi[rows] += np.einsum("rdk,rnk->rnd", Q, np.einsum("rkl,rnl->rnk", T, Qu))
+            Qu = u[None] @ Q                                            # (r, n, k), BLAS
+            phi[rows] += (Qu @ np.swapaxes(T, 1, 2)) @ np.swapaxes(Q, 1, 2)
         phi *= self.sqrt_alpha[:, None, :]
         phi += self.mu[:, None, :]
         logq = -0.5 * (self.logdet[:, None] + (u * u).sum(axis=1)[None, :] + self.D * np.log(2 * np.pi))
