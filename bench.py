@@ -38,8 +38,8 @@ UNIT = "grad-evals/s"
 
 WORKLOADS = {
     # name: (config key, genes per GPU by default, iterations per step, description)
-    "c2": ("c2", 11313, 2, "c2: examples/ ST-v1 geometry, splotch_stan_model 2-level Poisson+CAR, N=2473 spots, "
-                           "D=5016, all 11313 genes x 4 chains"),
+    "c2": ("c2", 11313, 2, "c2: examples/ ST-v1 geometry, splotch_stan_model 2-level Poisson+CAR, N=2594 spots "
+                           "(39 tissue sections of the 10 example arrays), D=5258, all 11313 genes x 4 chains"),
     "c3": ("c3", 592, 1, "c3: synthetic Visium 24x4992 spots, comp_splotch_stan_model 3-level ZIP+CAR K=10, "
                          "D=242142, gene slice x 4 chains"),
     "c4": ("c4", 296, 1, "c4: synthetic Visium-HD 4x317^2 bins, splotch_stan_model_csr 2-level ZIP+CAR, D=803989, "
