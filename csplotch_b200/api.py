@@ -380,9 +380,11 @@ class Sampler:
         total = self.cfg.num_warmup + self.cfg.num_samples
         chunk = total if not chunk else chunk
         done = 0
+        self.total_ms = 0.0                  # device time of the launches (CUDA events), for the batch report
         while done < total:
             n = min(chunk, total - done)
             self.advance(n, sync=True)
+            self.total_ms += self.last_ms()
             done += n
         return self
 

@@ -65,7 +65,7 @@ VINIT_NUM_WARMUP = 150     # bin/splotch_vinit:194
 
 
 def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chains, summary, seed=0,
-                 num_warmup=None, device=0, vinit=None, sig_figs=0):
+                 num_warmup=None, device=0, vinit=None, sig_figs=0, report=None):
     """`vinit`: None, or a dict of `pathfinder.pathfinder` options — every chain then starts at a Pathfinder draw of
     its gene (bin/splotch_vinit:137-182) instead of uniform(-2, 2)."""
     from . import api, _lib
@@ -118,7 +118,47 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
             stancsv.write_combined_csvs(paths, cols, diag[blk].reshape(len(blk), rows, 7),
                                         vals.reshape(len(blk), rows, -1), sig_figs=sig_figs)
             written += paths
+    if report:
+        import json
+        with open(report, "a") as f:
+            f.write(json.dumps(batch_report(s, gene_ids, status)) + "\n")
     return written, s
+
+
+def batch_report(s, gene_ids, status, ess_genes=8):
+    """One JSON-able dict per device batch (SURVEY.md §5 metrics: the reference only has CmdStan's progress lines):
+    work done, sampler health, and bulk-ESS / split-R-hat of the betas and scalar parameters of the first genes."""
+    from . import diagnostics as dg
+    diag, _, _ = s.draws()
+    cnt = s.counters()
+    nch, ns = s.nch, s.cfg.num_samples
+    ok = (np.asarray(status) == 0).all(axis=1)
+    d = diag[ok].reshape(-1, 7) if ok.any() else np.zeros((0, 7))
+    rep = {"genes": [int(gene_ids[0]), int(gene_ids[-1])], "n_genes": len(gene_ids), "chains": int(nch),
+           "num_warmup": int(s.cfg.num_warmup), "num_samples": int(ns), "device_ms": float(getattr(s, "total_ms", 0.0)),
+           "grad_evals": int(cnt["n_grad"]), "leapfrogs": int(cnt["n_leapfrog"]),
+           "failed_genes": [int(g) for g, o in zip(gene_ids, ok) if not o]}
+    if len(d):
+        rep.update(divergent_frac=float(d[:, 5].mean()), mean_treedepth=float(d[:, 3].mean()),
+                   treedepth_hist=np.bincount(d[:, 3].astype(int), minlength=11).tolist(),
+                   mean_stepsize=float(d[:, 2].mean()), mean_accept_stat=float(d[:, 1].mean()))
+    if ess_genes and ns >= 8 and ok.any():
+        ex = s.extract_small()
+        keys = [k for k in ex if k not in ("diag", "n_draws")]
+        ess, rhat = [], []
+        for i in np.nonzero(ok)[0][:ess_genes]:
+            cols = np.concatenate([ex[k][i].reshape(nch * ns, -1) for k in keys], axis=1).reshape(nch, ns, -1)
+            e, r = dg.summarize(cols)
+            ess.append(e)
+            rhat.append(r)
+        rep.update(ess_genes=len(ess), median_min_bulk_ess=float(np.median(ess)), median_max_rhat=float(np.median(rhat)))
+    return rep
+
+
+def output_exists(out_dir, g, summary):
+    """A finished gene: outputs are written to a temporary name and renamed, so existence means complete."""
+    base = os.path.join(out_dir, str(g // 100), "combined_%d" % g)
+    return any(os.path.exists(base + ext) for ext in ((".hdf5", ".hdf5.npz") if summary else (".csv",)))
 
 
 def main_vinit(argv=None):
@@ -143,6 +183,10 @@ def main(argv=None, vinit=False):
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--sig-figs", type=int, default=0,
                     help="significant digits in the CSV (CmdStan's sig_figs; 0 = shortest text that round-trips)")
+    ap.add_argument("--resume", action="store_true",
+                    help="skip genes whose combined_<g>.* already exists in the output directory")
+    ap.add_argument("--report", default=None, help="append one JSON line per device batch (work, sampler health, "
+                                                   "ESS / R-hat of the first genes) to this file")
     if vinit:
         ap.add_argument("--max-lbfgs-iters", type=int, default=1000, help="Pathfinder: L-BFGS iterations per path")
     a = ap.parse_args(argv)
@@ -162,6 +206,10 @@ def main(argv=None, vinit=False):
     if world > 1:
         gene_ids = shard.my_genes(sorted(gene_ids), world, rank)
         a.device = int(os.environ.get("LOCAL_RANK", str(rank)))
+        if not gene_ids:
+            return 0
+    if a.resume:
+        gene_ids = [g for g in gene_ids if not output_exists(a.o, g, a.s)]
         if not gene_ids:
             return 0
     # genes resident at once: bounded by device memory.  Per gene: 4 D-vectors + 6 N summary doubles per
@@ -188,10 +236,10 @@ def main(argv=None, vinit=False):
             if vinit:
                 sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device,
                              num_warmup=VINIT_NUM_WARMUP, vinit=dict(max_lbfgs_iters=a.max_lbfgs_iters),
-                             sig_figs=a.sig_figs)
+                             sig_figs=a.sig_figs, report=a.report)
             else:
                 sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device,
-                             sig_figs=a.sig_figs)
+                             sig_figs=a.sig_figs, report=a.report)
         except Exception as e:  # noqa: BLE001
             print("Error: Stan run failed! (%s)" % e, file=sys.stderr)
             rc = 1

@@ -214,3 +214,25 @@ def test_init_file_round_trip(golden_dir, tmp_path):
             bad.write_text(json.dumps({"tau.1": -3.0}))
             argv[6] = "init=" + str(bad)
             assert cli.cmdstan_shim(argv) == 1
+
+
+def test_resume_and_report(golden_dir, tmp_path):
+    """`--resume` skips genes whose output exists (file-level resume); `--report` appends one JSON line
+    per device batch with the work done, sampler health and ESS / R-hat."""
+    import json
+    data_dir = _c1_data_dir(golden_dir, tmp_path)
+    out, rep = str(tmp_path / "out"), str(tmp_path / "report.jsonl")
+    common = ["-d", data_dir, "-o", out, "-b", "comp_splotch_stan_model", "-n", "30", "-c", "2", "--seed", "5", "-s"]
+    assert cli.main(["-g", "3-4"] + common) == 0
+    stamp = {g: os.path.getmtime(os.path.join(out, "0", n)) for g in (3, 4) for n in os.listdir(os.path.join(out, "0"))
+             if n.startswith("combined_%d." % g)}
+    assert cli.main(["-g", "1-7", "--resume", "--report", rep] + common) == 0
+    lines = [json.loads(l) for l in open(rep)]
+    assert [l["genes"] for l in lines] == [[1, 2], [5, 7]]                       # 3 and 4 were not sampled again
+    for g in (3, 4):
+        assert stamp[g] == [os.path.getmtime(os.path.join(out, "0", n)) for n in os.listdir(os.path.join(out, "0"))
+                            if n.startswith("combined_%d." % g)][0]
+    for l in lines:
+        assert l["device_ms"] > 0 and l["grad_evals"] >= l["leapfrogs"] > 0 and l["failed_genes"] == []
+        assert sum(l["treedepth_hist"]) == l["n_genes"] * 2 * 30 and l["median_min_bulk_ess"] > 0
+    assert len([n for n in os.listdir(os.path.join(out, "0")) if n.startswith("combined_")]) == 7

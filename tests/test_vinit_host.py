@@ -25,6 +25,12 @@ class _Model:
         self.levels = (int(d["N_level_1"]), int(d.get("N_level_2", 0)), int(d.get("N_level_3", 0)))
         self.car, self.zi = int(d.get("car", 0)), int(d.get("zi", 0))
         self.nb = int(d.get("nb", 0)) if self.family == 1 else 0
+        L = sum(self.levels)
+        self.n_beta = L * self.C * self.K
+        self.n_scalar = self.dim - self.n_beta - (2 if self.car else 1) * self.N
+        self.n_small = self.n_beta + self.n_scalar
+        self.level_2_mapping = np.asarray(d.get("level_2_mapping", []), dtype=np.int64).reshape(-1)
+        self.level_3_mapping = np.asarray(d.get("level_3_mapping", []), dtype=np.int64).reshape(-1)
 
     column_names = api.Model.column_names
 
@@ -34,6 +40,8 @@ class _Batch:
         self.model, self.gene_id0 = model, gene_id0
         counts = np.asarray(counts).reshape(-1, model.N)
         self.G = len(counts)
+        self.beta_prior_mean = None if beta_prior_mean is None else np.asarray(beta_prior_mean, dtype=float).reshape(self.G, -1)
+        self.beta_prior_std = None if beta_prior_std is None else np.asarray(beta_prior_std, dtype=float).reshape(self.G, -1)
         self.o = []
         for g in range(self.G):
             d = dict(model._shared, counts=counts[g])
@@ -82,10 +90,27 @@ class _Sampler:
         return self._status, np.full((self.G, self.nch), self.cfg.num_warmup + self.cfg.num_samples)
 
     def draws(self, out=None):
-        return self._diag, None, None
+        # the non-spot block in the library's order: beta_raw[(i*C + j)*K + k] | scalars in declaration order
+        m = self.model
+        lay = {n: i for n, i, _ in api.param_layout(m)}
+        L = sum(m.levels)
+        idx = []
+        for i in range(L):
+            for j in range(m.C):
+                for k in range(m.K):
+                    idx.append(lay["beta_raw.%d.%d.%d" % (i + 1, j + 1, k + 1)] if m.family == 1
+                               else lay["beta_raw.%d.%d" % (i + 1, j + 1)])
+        idx += [i for n, i, t in api.param_layout(m) if t != "id"]
+        return self._diag, self._theta[..., idx], np.full((self.G, self.nch), self.cfg.num_samples, dtype=np.int32)
 
     def theta_draws(self):
         return self._theta
+
+    def counters(self):
+        return dict(n_leapfrog=int(self._diag[..., 4].sum()), n_grad=int(self._diag[..., 4].sum()), n_divergent=0,
+                    n_launches=1)
+
+    extract_small = api.Sampler.extract_small
 
 
 @pytest.fixture()
@@ -130,6 +155,30 @@ def test_splotch_vinit_control_flow(host_only, golden_dir, tmp_path):
     # plain `splotch` keeps num_warmup = num_samples and random starts (bin/splotch:131)
     assert cli.main(argv[:-2]) == 0
     assert host_only.started[-1][0] == 12 and host_only.started[-1][1] is None
+
+
+def test_resume_skips_finished_genes_and_report_lines(host_only, golden_dir, tmp_path):
+    """File-level resume ("skip genes whose combined_<g>.* exists") and the per-batch JSON report."""
+    data_dir = _c1_data_dir(golden_dir, tmp_path, (1, 2, 3))
+    out, rep = str(tmp_path / "out"), str(tmp_path / "report.jsonl")
+    common = ["-d", data_dir, "-o", out, "-b", "comp_splotch_stan_model", "-n", "16", "-c", "2", "--seed", "9"]
+    assert cli.main(["-g", "2"] + common) == 0
+    first = open(os.path.join(out, "0", "combined_2.csv")).read()
+    n0 = len(host_only.started)
+    assert cli.main(["-g", "1-3", "--resume", "--report", rep] + common) == 0
+    # gene 2 was not sampled again: two device batches (genes 1 and 3 are no longer contiguous), its file untouched
+    assert [s[1] for s in host_only.started[n0:]] == [None, None] and len(host_only.started) == n0 + 2
+    assert open(os.path.join(out, "0", "combined_2.csv")).read() == first
+    assert all(os.path.exists(os.path.join(out, "0", "combined_%d.csv" % g)) for g in (1, 2, 3))
+    assert cli.main(["-g", "1-3", "--resume", "--report", rep] + common) == 0 and len(host_only.started) == n0 + 2
+    lines = [json.loads(l) for l in open(rep)]
+    assert [l["genes"] for l in lines] == [[1, 1], [3, 3]]
+    for l in lines:
+        assert l["n_genes"] == 1 and l["chains"] == 2 and l["num_samples"] == 16 and l["failed_genes"] == []
+        assert l["grad_evals"] > 0 and sum(l["treedepth_hist"]) == 32 and 0 < l["mean_stepsize"] < 10
+        assert l["ess_genes"] == 1 and l["median_min_bulk_ess"] > 0 and l["median_max_rhat"] > 0.9
+    # summary mode looks for the summary file, not the CSV
+    assert not cli.output_exists(out, 2, summary=True) and cli.output_exists(out, 2, summary=False)
 
 
 def test_shim_pathfinder_then_reference_extraction_then_sample(host_only, golden_dir, tmp_path):
