@@ -92,8 +92,10 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        build()
-        _lib = C.CDLL(_LIB_PATH)
+        alt = os.environ.get("CSPLOTCH_ORACLE_LIB")       # e.g. the sanitizer build (`make -C oracle sanitize`)
+        if not alt:
+            build()
+        _lib = C.CDLL(alt or _LIB_PATH)
         _lib.orc_log_prob_grad.restype = C.c_double
         _lib.orc_nuts_batch.restype = C.c_int64
         _lib.orc_dim.restype = C.c_int32

@@ -18,12 +18,18 @@ class NutsConfig(C.Structure):
 
 
 def build():
+    """CSPLOTCH_EMUL_SAN=1: the same translation unit under AddressSanitizer + UndefinedBehaviorSanitizer (the vector
+    pool, the binary-counter stack and the window arithmetic of nuts_core.h are product code)."""
+    san = os.environ.get("CSPLOTCH_EMUL_SAN") == "1"
+    out = os.path.join(_HERE, "libemul_san.so") if san else _LIB
     srcs = [os.path.join(_HERE, "emul.cpp"), os.path.join(ROOT, "csplotch_b200", "csrc", "nuts_core.h"),
             os.path.join(ROOT, "csplotch_b200", "csrc", "philox.h")]
-    if (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-I" + os.path.join(ROOT, "csplotch_b200", "csrc"), "-o", _LIB, srcs[0]])
-    return _LIB
+    if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                 "-fno-omit-frame-pointer"] if san else ["-O2"]
+        subprocess.check_call(["/usr/bin/g++"] + flags + ["-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-I" + os.path.join(ROOT, "csplotch_b200", "csrc"), "-o", out, srcs[0]])
+    return out
 
 
 _lib = None
