@@ -1,0 +1,98 @@
+"""Live checks against the reference's own Python, imported read-only from /root/reference in the build container
+(skipped where it is absent, e.g. on the GPU box; the same import recipe as tests/golden/make_golden.py):
+a `combined_<g>.csv` written by this repo's native writer is parsed by the reference's `read_stan_csv`
+(/root/reference/splotch/utils.py:139-232, both its pandas and its line-by-line branch) and summarised by its
+`summarize_stan_hdf5` (utils.py:234-257, h5py replaced by a recording stand-in: h5py is not installed here) to the same
+arrays, groups and shapes as `stancsv.read_stan_csv` / `stancsv.summarize` give."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from csplotch_b200 import cli, stancsv
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "splotch", "utils.py")),
+                                reason="/root/reference not on this box")
+
+from tests.test_vinit_host import host_only, _c1_data_dir  # noqa: E402,F401  (fixture: oracle-backed device classes)
+
+
+@pytest.fixture(scope="module")
+def ref_utils():
+    before, path0 = dict(sys.modules), list(sys.path)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    U, _ = make_golden.load_reference()
+    yield U
+    # the stand-ins for the reference's absent imports (h5py, jax, ...) must not leak into other tests
+    for name in list(sys.modules):
+        if name not in before:
+            del sys.modules[name]
+    sys.path[:] = path0
+
+
+class _H5:
+    """Records what summarize_stan_hdf5 writes: {dataset name: array}."""
+    files = {}
+
+    def __init__(self, path, mode="r"):
+        self.path = path
+        _H5.files[path] = {}
+
+    def create_dataset(self, name, data=None):
+        _H5.files[self.path][name] = np.array(data)
+
+    def close(self):
+        pass
+
+
+def test_reference_reader_and_summariser_on_our_csv(ref_utils, host_only, golden_dir, tmp_path, monkeypatch):
+    data_dir = _c1_data_dir(golden_dir, tmp_path, (5,))
+    out = str(tmp_path / "out")
+    assert cli.main(["-g", "5", "-d", data_dir, "-o", out, "-b", "comp_splotch_stan_model", "-n", "20", "-c", "2",
+                     "--seed", "3"]) == 0
+    p = os.path.join(out, "0", "combined_5.csv")
+    variables = list(stancsv.SUMMARY_VARS)
+    mine = stancsv.read_stan_csv(p, variables)
+    for efficient in (False, True):
+        theirs = ref_utils.read_stan_csv(p, variables, efficient=efficient)
+        assert sorted(theirs) == sorted(mine)
+        for k in mine:
+            assert theirs[k].shape == mine[k].shape, (k, efficient)
+            if efficient:       # float() per token, like this repo's reader: exact
+                assert np.array_equal(theirs[k], mine[k]), k
+            else:               # pandas' default C float parser is not correctly rounded on 17-digit text (up to 1e-12 relative)
+                assert np.allclose(theirs[k], mine[k], rtol=1e-11, atol=1e-300), k
+    assert mine["beta_level_1"].shape == (40, 1, 14, 5) and mine["sigma"].shape == (40, 1)
+    # the summariser (what `splotch -s` / splotch_summarize_output leave for splotch_compile_lambdas / _betas)
+    monkeypatch.setattr(ref_utils, "h5py", type("h5py", (), {"File": _H5}))
+    h5 = str(tmp_path / "combined_5.hdf5")
+    ref_utils.summarize_stan_hdf5(p, h5)
+    theirs = _H5.files[h5]
+    want = stancsv.summarize(mine)
+    flat = {"%s/%s" % (k, s): a for k, d in want.items() for s, a in d.items()}
+    assert sorted(theirs) == sorted(flat)
+    for k in flat:
+        assert theirs[k].shape == flat[k].shape, k
+        assert np.allclose(theirs[k], flat[k], rtol=1e-13, atol=0), k
+    assert theirs["sigma/mean"].shape == (1,) and theirs["lambda/mean"].shape == (10,)
+    # and the file this repo writes for `-s` holds exactly those datasets
+    monkeypatch.delitem(sys.modules, "h5py", raising=False)          # the stand-in above is not an HDF5 library
+    path = stancsv.write_summary(str(tmp_path / "mine.hdf5"), want)
+    back = stancsv.read_summary(path)
+    assert sorted("%s/%s" % (k, s) for k, d in back.items() for s in d) == sorted(theirs)
+
+
+def test_reference_rdump_reader_on_our_writer(ref_utils, golden_dir, tmp_path):
+    """to_rdump of this repo -> read_rdump of the reference (utils.py:78-111), on a reference-generated gene."""
+    from csplotch_b200 import rdump
+    d = rdump.read_rdump(os.path.join(golden_dir, "c1", "data_3.R"))
+    p = str(tmp_path / "data_3.R")
+    rdump.to_rdump(d, p)
+    theirs = ref_utils.read_rdump(p)
+    assert sorted(theirs) == sorted(d)
+    for k in d:
+        assert np.array_equal(np.asarray(theirs[k]), np.asarray(d[k])), k
+    assert open(p).read() == open(os.path.join(golden_dir, "c1", "data_3.R")).read()      # byte-identical files
