@@ -171,11 +171,30 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "CPU restatement of the Stan models + Stan NUTS (oracle/), not CmdStan: CmdStan cannot be built here",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: file descriptor 1 is pointed at stderr for the rest of the
+    process (NCCL prints its version banner to stdout, libraries may chat), the line goes to the original descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -355,7 +374,7 @@ def main():
             line["cpu_baseline"] = {"value": cg / cdt, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample,
                                     "seconds": cdt,
                                     "note": "CPU restatement (oracle/), not CmdStan: CmdStan cannot be built in this image"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
