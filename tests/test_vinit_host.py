@@ -219,3 +219,27 @@ def test_shim_pathfinder_then_reference_extraction_then_sample(host_only, golden
         assert len(open(out).read().splitlines()) == 9
     # a method the executable does not have
     assert cli.cmdstan_shim(["/x/comp_splotch_stan_model", "optimize", "data", "file=" + path]) == 1
+
+
+def test_cli_shards_are_disjoint_and_shard_independent(host_only, golden_dir, tmp_path, monkeypatch):
+    """One process per GPU under torchrun (RANK / WORLD_SIZE): each rank samples its contiguous block of the gene list and
+    writes its own files; a gene's draws do not depend on the number of ranks (RNG keyed by the gene id)."""
+    data_dir = _c1_data_dir(golden_dir, tmp_path, (1, 2, 3, 4, 5))
+    common = ["-g", "1-5", "-d", data_dir, "-b", "comp_splotch_stan_model", "-n", "8", "-c", "2", "--seed", "21"]
+    one = str(tmp_path / "one")
+    assert cli.main(common + ["-o", one]) == 0
+    two = str(tmp_path / "two")
+    owners = {}
+    for rank in (0, 1):
+        monkeypatch.setenv("WORLD_SIZE", "2")
+        monkeypatch.setenv("RANK", str(rank))
+        monkeypatch.setenv("LOCAL_RANK", str(rank))
+        before = set(os.listdir(os.path.join(two, "0"))) if os.path.isdir(os.path.join(two, "0")) else set()
+        assert cli.main(common + ["-o", two]) == 0
+        for f in set(os.listdir(os.path.join(two, "0"))) - before:
+            owners[f] = rank
+    assert sorted(owners) == ["combined_%d.csv" % g for g in range(1, 6)]
+    assert [owners["combined_%d.csv" % g] for g in range(1, 6)] == [0, 0, 0, 1, 1]        # contiguous blocks, sizes 3 + 2
+    for g in range(1, 6):
+        assert open(os.path.join(one, "0", "combined_%d.csv" % g)).read() == \
+            open(os.path.join(two, "0", "combined_%d.csv" % g)).read()
