@@ -32,6 +32,8 @@ def _parse_numbers(txt: str) -> np.ndarray:
     txt = txt.strip()
     if not txt:
         return np.zeros(0, dtype=np.int64)
+    if "L" in txt:                      # R's own dump() marks integers as `3L`; to_rdump never does
+        txt = txt.replace("L", "")
     integral = not any(ch in txt for ch in ".eEnN")  # no '.', exponent, nan, inf
     toks = txt.split(",")
     if integral:
