@@ -243,3 +243,68 @@ def test_cli_shards_are_disjoint_and_shard_independent(host_only, golden_dir, tm
     for g in range(1, 6):
         assert open(os.path.join(one, "0", "combined_%d.csv" % g)).read() == \
             open(os.path.join(two, "0", "combined_%d.csv" % g)).read()
+
+
+def test_pystan_like_interface_semantics(host_only, golden_dir):
+    """simulation/fitting.py:35-51: `StanModel(file).sampling(data, iter, chains)` — `iter` counts warm-up + sampling and
+    warm-up defaults to iter // 2; `extract(permuted=True)['beta_level_1']` has the draw axis first."""
+    data = rdump.read_rdump(os.path.join(golden_dir, "c1", "data_7.R"))
+    fit = api.SplotchModel(file="/somewhere/stan/comp_splotch_stan_model.stan").sampling(data=data, iter=40, chains=3, seed=2,
+                                                                                         keep_draws=True)
+    nw, init = host_only.started[-1]
+    assert nw == 20 and init is None
+    ex = fit.extract(permuted=True)
+    assert ex["beta_level_1"].shape == (3 * 20, 1, 14, 5) and ex["sigma"].shape == (60,) and ex["lp__"].shape == (60,)
+    assert ex["log_lambda"].shape == (60, 10) and ex["psi"].shape == (60, 10)
+    assert set(fit.extract(pars=["tau", "a"])) == {"tau", "a"}
+    # the constrained values are those of write_array on the same draws (oracle): beta_level_1 = raw * std + mean
+    s = fit.sampler
+    wa = s.batch.write_array(s.theta_draws()[0].reshape(-1, s.model.dim))
+    cols = s.model.column_names()
+    j = cols.index("beta_level_1.1.3.2")
+    assert np.allclose(ex["beta_level_1"][:, 0, 2, 1], wa[:, j], rtol=1e-12, atol=1e-12)
+    assert np.allclose(ex["tau"], wa[:, cols.index("tau.1")], rtol=1e-12)
+    assert np.allclose(ex["theta"], wa[:, cols.index("theta.1")], rtol=1e-12)
+    d = fit.sampler_diagnostics()
+    assert d["treedepth__"].shape == (60,) and d["treedepth__"].max() <= 10
+    fit = api.SplotchModel(model_name="comp_splotch_stan_model").sampling(data=data, iter=30, warmup=25, chains=1)
+    assert host_only.started[-1][0] == 25 and fit.extract()["sigma"].shape == (5,)
+
+
+@pytest.mark.parametrize("family", ["splotch_stan_model", "comp_splotch_stan_model", "splotch_stan_model_csr"])
+def test_extract_small_equals_write_array_on_three_levels(host_only, family):
+    """The host-side constraining of the non-spot block (`Sampler.extract_small`: hierarchical betas from beta_raw,
+    sigma_level_k and the level maps; stan/*.stan transformed parameters) against the oracle's write_array columns."""
+    from csplotch_b200 import synth
+    shared = synth.shared_tiny(seed=5, family=family, n_levels=3, zi=1, car=1)
+    genes = synth.simulate_counts(shared, 2, 6)
+    if family == "comp_splotch_stan_model":
+        rng = np.random.default_rng(1)
+        genes["beta_prior_mean"] = rng.normal(0, 1, genes["beta_prior_mean"].shape)
+        genes["beta_prior_std"] = rng.uniform(0.5, 3, genes["beta_prior_std"].shape)
+    model = api.Model(shared, family)
+    batch = api.Batch(model, genes["counts"], genes.get("beta_prior_mean"), genes.get("beta_prior_std"))
+    s = api.Sampler(batch, api.nuts_cfg(6, 5, 2, seed=3, keep_draws=True)).run()
+    ex = s.extract_small()
+    cols = model.column_names()
+    for g in range(2):
+        wa = batch.write_array(s.theta_draws()[g].reshape(-1, model.dim), gene_of=np.full(10, g))
+        got = stancsv_like(ex, g)
+        for name, arr in got.items():
+            j = cols.index(name)
+            assert np.allclose(arr, wa[:, j], rtol=1e-12, atol=1e-12), (family, name)
+
+
+def stancsv_like(ex, g):
+    """{dotted column name: draws} of every beta_level_* / scalar entry of extract_small for gene g."""
+    out = {}
+    for key, arr in ex.items():
+        if key in ("diag", "n_draws"):
+            continue
+        a = arr[g]
+        if a.ndim == 1:
+            out[key if key == "sigma" else key + ".1"] = a
+            continue
+        for idx in np.ndindex(*a.shape[1:]):
+            out[key + "." + ".".join(str(i + 1) for i in idx)] = a[(slice(None),) + idx]
+    return out
