@@ -295,8 +295,8 @@ def pathfinder(target, *, num_paths: int = 4, num_draws: int = 1000, num_out: in
     """Multi-path Pathfinder of every gene of `target` (G genes x `num_paths` paths in one batched L-BFGS).
 
     `num_draws` draws are taken from the best approximation of every path; `num_out` (default `num_draws`) draws per
-    gene are returned after PSIS resampling over the gene's paths (`psis_resample=False`: the first draws of each
-    path in turn).  `init`: optional (G, P, D) starting points.  `eval_rows` bounds the rows of one target call
+    gene are returned after PSIS resampling over the gene's paths (`psis_resample=False` or a single path: the draws
+    of each path in turn, unweighted).  `init`: optional (G, P, D) starting points.  `eval_rows` bounds the rows of one target call
     (default: 512 MB of parameter vectors).
     """
     D, G, P, J = target.dim, target.G, int(num_paths), int(history_size)
@@ -491,7 +491,7 @@ def pathfinder(target, *, num_paths: int = 4, num_draws: int = 1000, num_out: in
                 lpas.append(logq[0])
                 where.append(np.stack([np.full(nb, r), np.arange(b0, b0 + nb)], axis=1))
         lps, lpas, where = np.concatenate(lps), np.concatenate(lpas), np.concatenate(where)
-        if psis_resample:
+        if psis_resample and P > 1:              # single-path Pathfinder returns its draws as they are (Stan)
             logw, pareto_k[gi] = psis_log_weights(lps - lpas)
             rng = _row_rng(seed, target.gene_id0 + gi, 255)
             pick = rng.choice(len(lps), size=num_out, replace=True, p=np.exp(logw))

@@ -151,6 +151,15 @@ def test_result_of_a_gene_does_not_depend_on_the_batch():
     assert not np.array_equal(other.draws[0], one.draws[0])
 
 
+def test_single_path_returns_its_draws_unweighted():
+    t = GaussTarget(1, 5, seed=4)
+    r = pf.pathfinder(t, num_paths=1, num_draws=300, seed=1)
+    assert (r.path == 1).all() and not np.isfinite(r.pareto_k[0])            # no importance resampling happened
+    assert len(np.unique(r.lp[0])) == 300                                       # every draw once, none duplicated
+    r2 = pf.pathfinder(t, num_paths=2, num_draws=300, seed=1, psis_resample=False)
+    assert sorted(np.unique(r2.path[0])) == [1, 2] and len(np.unique(r2.lp[0])) == 300
+
+
 def test_failed_paths_and_non_finite_densities():
     class Hostile(GaussTarget):
         def lp_grad(self, th, go):
