@@ -398,7 +398,8 @@ def pathfinder(target, *, num_paths: int = 4, num_draws: int = 1000, num_out: in
             fin = u[done]
             xn[fin], fn[fin], gn[fin] = xt[done], ft[done], gt[done]
             t = np.where(np.isfinite(hi), 0.5 * (lo + hi), 2.0 * np.maximum(lo, t))
-            und &= (hi - lo) > 1e-16 * np.maximum(hi, 1e-300)
+            with np.errstate(invalid="ignore"):
+                und &= ~np.isfinite(hi) | ((hi - lo) > 1e-16 * np.maximum(hi, 1e-300))   # bracket collapsed
         moved = have | ~und
         moved &= np.isfinite(fn)
         failed = act[~moved]
