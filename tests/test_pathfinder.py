@@ -286,3 +286,28 @@ def _c1_columns(model, n_out):
     cols += ["beta_level_1.%d.%d.%d" % (1, j + 1, k + 1) for k in range(K) for j in range(C)]
     assert len(cols) == n_out, (len(cols), n_out)
     return cols
+
+
+def test_vinit_chains_sample_the_same_posterior(c1_target):
+    """bin/splotch_vinit end to end on the CPU oracle: Pathfinder starts + 150 warm-up transitions give the same
+    posterior as the plain run (N warm-up transitions from uniform(-2, 2)) — means within 5 Monte Carlo standard
+    errors for every beta_level_1 entry and scalar of the reference's c1 gene."""
+    import oracle
+    from csplotch_b200 import diagnostics as dg
+    t, o = c1_target, c1_target.o[0]
+    n, chains = 400, 4
+    r = pf.pathfinder(t, num_paths=chains, num_draws=1000, num_out=chains, seed=12, max_lbfgs_iters=200)
+    runs = {}
+    for name, nw, inits in (("plain", n, [None] * chains), ("vinit", 150, list(r.draws[0]))):
+        cfg = oracle.nuts_cfg(nw, n, seed=31)
+        outs = [o.nuts(cfg, gene_id=1, chain_id=c + 1, q_init=inits[c]) for c in range(chains)]
+        assert all(x["status"] == 0 for x in outs)
+        th = np.stack([x["draws"][:, 7:] for x in outs])                        # (chains, n, D) unconstrained
+        wa = np.stack([[o.write_array(q) for q in ch] for ch in th])            # constrained, CSV column order
+        runs[name] = wa[:, :, 10:10 + 70 + 4]                                    # beta_raw (70) | tau a sigma theta
+    worst = 0.0
+    for j in range(runs["plain"].shape[2]):
+        a, b = runs["plain"][:, :, j], runs["vinit"][:, :, j]
+        se = np.sqrt(a.var() / dg.ess_bulk(a) + b.var() / dg.ess_bulk(b))
+        worst = max(worst, abs(a.mean() - b.mean()) / se)
+    assert worst < 5.0, worst
