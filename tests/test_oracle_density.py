@@ -172,3 +172,22 @@ def test_negative_binomial_branch(zi, nb):
     assert np.allclose(o.unconstrain(wa[:o.dim]), th, rtol=1e-12, atol=1e-12)
     phi = 1e-6 + np.exp(th[N + (o.dim - 2 * N - (4 + zi + 1)) + 4 + zi])
     assert np.allclose(wa[o.dim + N:o.dim + 2 * N], phi)           # phi_arr follows log_lambda
+
+
+def test_oracle_reproduces_committed_known_answers():
+    """tests/golden/c1_lpgrad.npz (made by tests/golden/make_lpgrad_golden.py; oracle output accepted only where the
+    autograd transcription agreed): a change of the oracle that moves lp or the gradient on the reference's c1 genes
+    fails here, and the GPU path is held to the same file (tests/test_gpu_parity.py)."""
+    import os
+    from csplotch_b200 import rdump
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(gdir, "c1_lpgrad.npz"))
+    assert z["theta"].shape == (7, 3, 94)
+    for g in range(7):
+        o = oracle.Oracle(rdump.read_rdump(os.path.join(gdir, "c1", "data_%d.R" % (g + 1))), "comp_splotch_stan_model")
+        for i in range(3):
+            lp, grad = o.log_prob_grad(z["theta"][g, i])
+            assert abs(lp - z["lp_jacobian"][g, i]) <= 1e-13 * max(1.0, abs(lp))
+            assert np.max(np.abs(grad - z["grad_jacobian"][g, i]) / np.maximum(1.0, np.abs(grad))) < 1e-13
+            lp0 = o.log_prob_grad(z["theta"][g, i], jacobian=False, want_grad=False)
+            assert abs(lp0 - z["lp_no_jacobian"][g, i]) <= 1e-13 * max(1.0, abs(lp0))
