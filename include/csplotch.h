@@ -116,7 +116,8 @@ int32_t csplotch_abi_version(void);
 int32_t csplotch_device_count(void);
 int32_t csplotch_set_device(int32_t device);
 
-/* Page-locked host buffers for arrays handed to / filled by the calls below (optional: every host pointer may
+/* (no reference counterpart: /root/reference/bin/splotch moves data through files and pipes)
+ * Page-locked host buffers for arrays handed to / filled by the calls below (optional: every host pointer may
  * also be ordinary pageable memory).  The reference moves these data through files and pipes; here they cross
  * PCIe, and a pinned buffer makes each transfer a single DMA.  csplotch_host_free(NULL) is a no-op. */
 int32_t csplotch_host_alloc(uint64_t bytes, void **out);
@@ -147,17 +148,24 @@ int32_t csplotch_log_prob_grad_dev(csplotch_batch *b, const double *theta_dev, c
                                    int32_t B, double *lp_dev, double *grad_dev, int32_t jacobian,
                                    void *stream);
 
-/* ---- model.write_array(): constrained params + transformed params, CSV column order --- */
+/* ---- model.write_array(): constrained params + transformed params, CSV column order ---
+ * (parameters{} / transformed parameters{} of stan/splotch_stan_model.stan:74-130, comp_…:81-150; the columns that
+ * read_stan_csv maps back by dotted name, /root/reference/splotch/utils.py:196-224) */
 int32_t csplotch_write_array(csplotch_batch *b, const double *theta, const int32_t *gene_of, int32_t B,
                              double *out /* [B][n_outputs] */);
 
-/* ---- expl_leapfrog with a diagonal metric, fixed step (tier-2 parity) ------------------ */
+/* ---- expl_leapfrog with a diagonal metric, fixed step (tier-2 parity) ------------------
+ * (upstream stan::mcmc::expl_leapfrog + diag_e_metric, the integrator behind /root/reference/bin/splotch:131;
+ * not in the reference tree — a test hook, no reference call site binds it) */
 /* theta0,p0,inv_metric: [B][dim]; outputs [B][dim], H_out[B] */
 int32_t csplotch_leapfrog_fixed(csplotch_batch *b, const double *theta0, const double *p0,
                                 const double *inv_metric, const int32_t *gene_of, int32_t B, double eps,
                                 int32_t n_steps, double *theta_out, double *p_out, double *H_out);
 
-/* ---- `BINARY sample ...`: hmc_nuts_diag_e_adapt over all genes x chains ---------------- */
+/* ---- `BINARY sample ...`: hmc_nuts_diag_e_adapt over all genes x chains ----------------
+ * (/root/reference/bin/splotch:129-133: one process per chain with num_samples, num_warmup, id;
+ * /root/reference/bin/splotch_vinit:194 adds init=FILE.json -> csplotch_sampler_init;
+ * /root/reference/simulation/fitting.py:35-48: pystan .sampling(iter, chains)) */
 void csplotch_nuts_cfg_default(csplotch_nuts_cfg *cfg);
 int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nuts_cfg *cfg, csplotch_sampler **out);
 void csplotch_sampler_destroy(csplotch_sampler *s);
@@ -180,7 +188,8 @@ int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out8);
 /* per-chain status [G][num_chains]: 0 ok, 1 initialisation failed, 2 step size search failed */
 int32_t csplotch_sampler_status(csplotch_sampler *s, int32_t *status, int32_t *iters_done);
 
-/* sampling draws so far.
+/* sampling draws so far: the rows CmdStan writes to `output file=…csv` and the wrapper concatenates
+ * (/root/reference/bin/splotch:131,138-140).
  * diag  [G][num_chains][num_samples][7]  lp__,accept_stat__,stepsize__,treedepth__,n_leapfrog__,divergent__,energy__
  * small [G][num_chains][num_samples][n_small]  the UNCONSTRAINED non-spot block: beta_raw[(i*C + j)*K + k]
  *        (level-major rows, the same for all three families) followed by tau, a, sigma, sigma_level_2,
