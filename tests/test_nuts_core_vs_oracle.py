@@ -73,3 +73,38 @@ def test_max_depth_and_divergence_paths():
         got = emul.nuts_run(fn, ctx, D, cfg, gene_id=0, chain_id=1, q_init=q0)
         assert np.array_equal(got["draws"][:, 3:6], draws_o[:, 3:6])
         assert np.allclose(got["draws"], draws_o, rtol=1e-9, atol=1e-9)
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None, derandomize=True)
+@given(D=st.integers(1, 12), log_sd=st.lists(st.floats(-2, 2), min_size=12, max_size=12),
+       nw=st.sampled_from([0, 1, 5, 19, 20, 21, 33, 99, 149, 150, 151, 200]), seed=st.integers(0, 2**31 - 1),
+       max_depth=st.sampled_from([1, 2, 5, 10]), delta=st.sampled_from([0.6, 0.8, 0.95]),
+       chunk=st.integers(0, 17), gene=st.integers(0, 40000), chain=st.integers(1, 8))
+def test_random_gaussians_windows_and_depths(D, log_sd, nw, seed, max_depth, delta, chunk, gene, chain):
+    """Warm-up lengths around every branch of Stan's window arithmetic (< 20: step size only; < 150: the 15 % / 10 %
+    rule; the stretched last window), tree depths from 1 to 10, any launch chunking: the iterative tree / vector pool /
+    reservoir proposal of nuts_core.h and the oracle's recursive restatement give the same draws, step size and metric."""
+    sd = 10.0 ** np.array(log_sd[:D])
+    arr, ctx = _gauss_ctx(sd)
+    ns = 12
+    cfg = oracle.nuts_cfg(nw, ns, seed=seed, max_depth=max_depth, delta=delta)
+    fn = C.cast(oracle.lib().orc_gauss_density, C.c_void_p)
+    draws_o = np.zeros((ns, 7 + D)); inv_o = np.empty(D); eps_o = C.c_double(0); ng = C.c_int64(0)
+    st_o = oracle.lib().orc_nuts_generic(fn, ctx, C.c_int32(D), C.byref(cfg), C.c_uint32(gene), C.c_uint32(chain), None,
+                                         C.c_int32(0), draws_o.ctypes.data_as(C.c_void_p),
+                                         inv_o.ctypes.data_as(C.c_void_p), C.byref(eps_o), C.byref(ng))
+    got = emul.nuts_run(fn, ctx, D, cfg, gene_id=gene, chain_id=chain, chunk=chunk)
+    assert got["status"] == st_o
+    if st_o != 0:
+        return
+    assert np.array_equal(got["draws"][:, 3:6], draws_o[:, 3:6])
+    assert np.allclose(got["draws"], draws_o, rtol=1e-8, atol=1e-8)
+    assert np.allclose(got["inv_metric"], inv_o, rtol=1e-10)
+    assert abs(got["stepsize"] - eps_o.value) <= 1e-10 * eps_o.value
+    # work accounting: the product counts the gradient evaluations it performs — one at the current point per step-size
+    # search, reused by every attempt — while the oracle, like upstream, re-evaluates it per attempt; so the oracle's
+    # count can only be the larger one (the rate the product reports is not inflated)
+    assert 0 <= ng.value - got["n_grad"] <= 8 + ng.value // 5
