@@ -13,3 +13,6 @@ for shape in c2 c3; do
   bash scripts/ncu_capture.sh nuts_$shape k_nuts_advance scripts/profile_nuts.py $shape $G 2
   python scripts/traffic_from_ncu.py nuts_$shape $shape
 done
+# splotch_vinit against plain splotch on c2 genes: re-measure after the Pathfinder line-search fix,
+# with CmdStan's iteration cap (1000) replaced by 200 to bound the host time
+python scripts/vinit_compare.py 16 200 200 > gpurun_out/vinit_compare_c2.json 2> gpurun_out/vinit_compare_c2.err; cut -c1-400 gpurun_out/vinit_compare_c2.json
