@@ -76,14 +76,19 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
                       genes.get("beta_prior_std") if fam == 1 else None, gene_id0=int(gene_ids[0]))
     nw = num_samples if num_warmup is None else num_warmup          # bin/splotch:131 num_warmup=num_samples
     cfg = api.nuts_cfg(nw, num_samples, num_chains, seed=seed, keep_draws=not summary)
-    theta_init, pf_failed = None, np.zeros(len(gene_ids), dtype=bool)
+    theta_init, pf_failed, pf_rep = None, np.zeros(len(gene_ids), dtype=bool), None
     if vinit is not None:
+        import time
         from . import pathfinder
         opts = dict(num_paths=num_chains, num_draws=VINIT_NUM_DRAWS, num_out=num_chains, seed=seed)
         opts.update(vinit)
+        t0 = time.time()
         pf = pathfinder.pathfinder(pathfinder.BatchTarget(batch), **opts)
         pf_failed = ~np.isfinite(pf.lp).all(axis=1)
         theta_init = pf.draws
+        pf_rep = {"seconds": time.time() - t0, "lp_grad_evals": int(pf.n_lp_grad), "lp_evals": int(pf.n_lp),
+                  "median_lbfgs_iters": float(np.median(pf.lbfgs_iters)), "median_best_iter": float(np.median(pf.best_iter)),
+                  "median_pareto_k": float(np.median(pf.pareto_k)), "failed_genes": [int(g) for g, f in zip(gene_ids, pf_failed) if f]}
     s = api.Sampler(batch, cfg, theta_init=theta_init).run(chunk=50)
     status, iters = s.status()
     cols = model.column_names()
@@ -121,7 +126,10 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
     if report:
         import json
         with open(report, "a") as f:
-            f.write(json.dumps(batch_report(s, gene_ids, status)) + "\n")
+            rep = batch_report(s, gene_ids, status)
+            if pf_rep is not None:
+                rep["pathfinder"] = pf_rep
+            f.write(json.dumps(rep) + "\n")
     return written, s
 
 

@@ -136,7 +136,11 @@ def test_splotch_vinit_control_flow(host_only, golden_dir, tmp_path):
     out = str(tmp_path / "out")
     argv = ["-g", "2-3", "-d", data_dir, "-o", out, "-b", "/opt/bin/comp_splotch_stan_model", "-n", "12", "-c", "2",
             "--seed", "4", "--max-lbfgs-iters", "40"]
-    assert cli.main_vinit(argv) == 0
+    rep = str(tmp_path / "vinit.jsonl")
+    assert cli.main_vinit(argv + ["--report", rep]) == 0
+    (line,) = [json.loads(l) for l in open(rep)]
+    assert line["num_warmup"] == 150 and line["pathfinder"]["lp_grad_evals"] > 0 and line["pathfinder"]["failed_genes"] == []
+    assert line["pathfinder"]["median_lbfgs_iters"] <= 40
     (nw, init), = host_only.started
     assert nw == 150 and init.shape == (2, 2, 94)                              # bin/splotch_vinit:194 num_warmup=150
     # the chains start at Pathfinder draws: far better than uniform(-2, 2) starts
