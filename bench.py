@@ -106,13 +106,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(workload: str, genes_per_gpu: int, rank: int):
+def make_inputs(workload: str, genes_per_gpu: int, rank: int, head_only: bool = False):
+    """`head_only`: just the first generation chunk of the gene list (the generator is chunk-wise deterministic, so
+    these are the same genes as the head of the full list) — all the CPU legs ever touch."""
     from csplotch_b200 import synth
     key = WORKLOADS[workload][0]
     cfg = synth.CONFIGS[key]
     shared = cfg["shared"]()
+    chunk = max(16, (1 << 22) // int(np.sum(shared["N_spots"])))
+    if head_only:
+        genes_per_gpu = min(genes_per_gpu, chunk)
     # every rank owns a different slice of the gene list (seeded by global gene index block)
-    genes = synth.simulate_counts(shared, genes_per_gpu, cfg["seed"] + 1000 * rank, chunk=max(16, (1 << 22) // int(np.sum(shared["N_spots"]))))
+    genes = synth.simulate_counts(shared, genes_per_gpu, cfg["seed"] + 1000 * rank, chunk=chunk)
     return cfg["family"], shared, genes
 
 
@@ -150,7 +155,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     # the same genes as the cpu_baseline leg of the GPU arm: the head of the workload's gene list
-    family, shared, genes = make_inputs(args.workload, WORKLOADS[args.workload][1], 0)
+    family, shared, genes = make_inputs(args.workload, WORKLOADS[args.workload][1], 0, head_only=True)
     nthr = os.cpu_count() or 1
     N = int(np.sum(shared["N_spots"]))
     iters = args.cpu_iters or cpu_iters_for(family, shared, genes, nthr, 120.0 / max(1, args.steps + args.warmup))

@@ -1,0 +1,63 @@
+"""Host-side pieces of bench.py that the driver's contract depends on, without a GPU: the clocks / throttle-reason
+sampler (a stand-in nvidia-smi on PATH), the roofline peak lookup, and the reference arm's JSON line (stdout carries
+that line and nothing else)."""
+import json
+import os
+import stat
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_clock_sampler_parses_clocks_and_reasons(tmp_path, monkeypatch):
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\n"
+                    "echo '0, 1965, 1965, 410.2, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active'\n"
+                    "echo '0, 1950, 1965, 690.0, 0x0000000000000004, Not Active, Not Active, Not Active, Active'\n"
+                    "echo '0, 1200, 1965, 700.1, 0x0000000000000040, Not Active, Active, Not Active, Active'\n"
+                    "echo 'garbage line'\n"
+                    "sleep 30\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    cs = bench.ClockSampler(0)
+    cs.start()
+    time.sleep(0.5)
+    out = cs.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
+
+
+def test_clock_sampler_without_nvidia_smi(monkeypatch, tmp_path):
+    monkeypatch.setenv("PATH", str(tmp_path))
+    cs = bench.ClockSampler(0)
+    cs.start()
+    assert cs.stop()["reasons"] == ["nvidia-smi unavailable"]
+
+
+def test_roofline_peak_is_the_measured_one():
+    peak, src = bench.peaks()
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        assert peak == float(json.load(open(p))["hbm_gbs"]) and src.startswith("measured")
+    else:
+        assert src.startswith("fallback") and 6000 < peak < 8000
+
+
+def test_reference_arm_prints_exactly_one_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-iters", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "grad_evals_per_sec" and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # under torchrun only rank 0 works
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout == ""
