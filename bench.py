@@ -121,6 +121,45 @@ def make_inputs(workload: str, genes_per_gpu: int, rank: int, head_only: bool = 
     return cfg["family"], shared, genes
 
 
+def ess_leg(api, model, genes, G, n, chains=4, seed=11, ess_genes=64):
+    """Second half of BASELINE.json's metric: genes / hour to bulk-ESS >= 400.  A complete `splotch -n N -c 4` job
+    (N warm-up + N sampling transitions from initialisation, /root/reference/bin/splotch:131) of the first G genes;
+    rate = G / device time of the launches, scaled by the fraction of (the first `ess_genes`) genes whose minimum
+    rank-normalised bulk-ESS reaches 400 — over every beta_level_* entry and scalar parameter (the metric as
+    stated), and over the betas alone (what the reference's downstream Bayes factors use; the variance scalars of
+    these models mix slowly in any implementation)."""
+    from csplotch_b200 import diagnostics as dg
+    pm = genes["beta_prior_mean"][:G] if "beta_prior_mean" in genes else None
+    ps = genes["beta_prior_std"][:G] if "beta_prior_std" in genes else None
+    batch = api.Batch(model, genes["counts"][:G], pm, ps)
+    s = api.Sampler(batch, api.nuts_cfg(n, n, chains, seed=seed)).run(chunk=50)
+    seconds = s.total_ms * 1e-3
+    status, _ = s.status()
+    ex = s.extract_small()
+    bkeys = [k for k in ex if k.startswith("beta_level")]
+    skeys = [k for k in ex if k not in bkeys and k not in ("diag", "n_draws")]
+    ess_all, ess_beta, rhat_beta = [], [], []
+    for g in range(min(G, ess_genes)):
+        if (status[g] != 0).any():
+            ess_all.append(0.0); ess_beta.append(0.0); rhat_beta.append(float("inf"))
+            continue
+        cb = np.concatenate([ex[k][g].reshape(chains * n, -1) for k in bkeys], axis=1).reshape(chains, n, -1)
+        cs = np.concatenate([ex[k][g].reshape(chains * n, -1) for k in skeys], axis=1).reshape(chains, n, -1)
+        eb, rb = dg.summarize(cb)
+        es, _ = dg.summarize(cs)
+        ess_all.append(min(eb, es)); ess_beta.append(eb); rhat_beta.append(rb)
+    ess_all, ess_beta = np.array(ess_all), np.array(ess_beta)
+    gph = G / seconds * 3600.0 if seconds > 0 else 0.0
+    out = {"genes": int(G), "chains": int(chains), "num_warmup": int(n), "num_samples": int(n), "device_seconds": seconds,
+           "genes_per_hour": gph, "grad_evals": int(s.counters()["n_grad"]), "genes_evaluated_for_ess": int(len(ess_all)),
+           "genes_per_hour_to_ess400": gph * float((ess_all >= 400).mean()), "median_min_bulk_ess": float(np.median(ess_all)),
+           "beta_only": {"genes_per_hour_to_ess400": gph * float((ess_beta >= 400).mean()),
+                         "median_min_bulk_ess": float(np.median(ess_beta)), "median_max_rhat": float(np.median(rhat_beta))}}
+    if hasattr(s, "close"):
+        s.close(); batch.close()
+    return out
+
+
 def cpu_reference_run(family, shared, genes, iters, n_threads, n_chains=4):
     """Bounded CPU sample: n_threads gene-chains (one thread each, like CmdStan's one process per
     chain) for `iters` warm-up transitions from initialisation; returns (grads, seconds, description)."""
@@ -213,6 +252,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-genes", type=int, default=0)
     ap.add_argument("--e2e-iters", type=int, default=0, help="NUTS transitions per chain in one e2e step")
+    ap.add_argument("--ess-genes", type=int, default=0,
+                    help="also run a full `splotch -n N -c 4` job of this many genes per GPU and report genes/hour to "
+                         "bulk-ESS >= 400 (off by default: it adds minutes)")
+    ap.add_argument("--ess-n", type=int, default=200, help="N of that job (the reference's README uses -n 200)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 3) if os.environ.get("CSPLOTCH_BENCH_STRICT", "1") == "1" else args.warmup
@@ -329,6 +372,19 @@ def main():
     e_dt = time.time() - t0
     note("e2e arm: %d timed steps done" % e_steps)
 
+    # ---- optional: genes / hour to bulk-ESS >= 400 (second half of the BASELINE metric) -----------------
+    ess = None
+    if args.ess_genes > 0:
+        ess = ess_leg(api, model, genes, min(G, args.ess_genes), args.ess_n, args.chains)
+        note("ESS leg done (%d genes, -n %d)" % (ess["genes"], args.ess_n))
+        if world > 1:                     # whole-job rate: ranks work on disjoint genes at the same time
+            t = torch.tensor([ess["genes_per_hour"], ess["genes_per_hour_to_ess400"],
+                              ess["beta_only"]["genes_per_hour_to_ess400"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ess["genes_per_hour"], ess["genes_per_hour_to_ess400"] = float(t[0]), float(t[1])
+            ess["beta_only"]["genes_per_hour_to_ess400"] = float(t[2])
+            ess["note"] = "rates summed over %d GPUs; ESS statistics are rank 0's" % world
+
     # ---- reduce over ranks ---------------------------------------------------------------------------
     if world > 1:
         t = torch.tensor([ms_dev, e_dt], dtype=torch.float64, device="cuda")
@@ -372,6 +428,8 @@ def main():
             "clocks": clk,
             "leapfrogs": leaps, "grad_evals": grads, "wall_s": t_wall,
         }
+        if ess is not None:
+            line["ess"] = ess
         if world == 1 and not args.no_cpu:
             nthr = os.cpu_count() or 1
             cg, cdt, sample = cpu_reference_run(family, shared, genes,

@@ -16,3 +16,5 @@ done
 # splotch_vinit against plain splotch on c2 genes: re-measure after the Pathfinder line-search fix,
 # with CmdStan's iteration cap (1000) replaced by 200 to bound the host time
 python scripts/vinit_compare.py 16 200 200 > gpurun_out/vinit_compare_c2.json 2> gpurun_out/vinit_compare_c2.err; cut -c1-400 gpurun_out/vinit_compare_c2.json
+# second half of the BASELINE metric inside the bench line itself (opt-in leg): genes / hour to bulk-ESS >= 400
+python bench.py --no-cpu --steps 2 --ess-genes 592 --ess-n 200 > gpurun_out/bench_c2_ess.json 2> gpurun_out/bench_c2_ess.err; python -c "import json;d=json.load(open('gpurun_out/bench_c2_ess.json'));print('ess', d['ess'])"

@@ -61,3 +61,32 @@ def test_reference_arm_prints_exactly_one_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and r.stdout == ""
+
+
+def test_ess_leg_with_oracle_backed_device_classes(monkeypatch):
+    """`bench.py --ess-genes`: the genes/hour-to-ESS>=400 leg on stand-ins for the device classes (tests only), so the
+    bookkeeping — which draws enter which ESS, rates, failed chains — is checked without a GPU."""
+    import numpy as np
+    from csplotch_b200 import api, rdump
+    from tests import test_vinit_host as fakes
+
+    class Sampler(fakes._Sampler):
+        def run(self, chunk=None):
+            super().run(chunk)
+            self.total_ms = 1800.0               # 1.8 s of "device time"
+            return self
+
+    monkeypatch.setattr(api, "Model", fakes._Model)
+    monkeypatch.setattr(api, "Batch", fakes._Batch)
+    monkeypatch.setattr(api, "Sampler", Sampler)
+    gdir = os.path.join(ROOT, "tests", "golden", "c1")
+    datas = [rdump.read_rdump(os.path.join(gdir, "data_%d.R" % g)) for g in (1, 2, 3)]
+    shared = {k: v for k, v in datas[0].items() if k not in rdump.GENE_KEYS}
+    genes = {k: np.stack([d[k] for d in datas]) for k in rdump.GENE_KEYS}
+    model = api.Model(shared, "comp_splotch_stan_model")
+    out = bench.ess_leg(api, model, genes, 3, 60, chains=4, ess_genes=2)
+    assert out["genes"] == 3 and out["genes_evaluated_for_ess"] == 2 and out["num_warmup"] == out["num_samples"] == 60
+    assert abs(out["genes_per_hour"] - 3 / 1.8 * 3600) < 1e-6 and out["grad_evals"] > 0
+    assert 0 <= out["genes_per_hour_to_ess400"] <= out["beta_only"]["genes_per_hour_to_ess400"] <= out["genes_per_hour"]
+    assert 0 < out["median_min_bulk_ess"] <= out["beta_only"]["median_min_bulk_ess"] < 4 * 60 * 3
+    assert out["beta_only"]["median_max_rhat"] > 0.95
