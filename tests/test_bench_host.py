@@ -90,3 +90,31 @@ def test_ess_leg_with_oracle_backed_device_classes(monkeypatch):
     assert 0 <= out["genes_per_hour_to_ess400"] <= out["beta_only"]["genes_per_hour_to_ess400"] <= out["genes_per_hour"]
     assert 0 < out["median_min_bulk_ess"] <= out["beta_only"]["median_min_bulk_ess"] < 4 * 60 * 3
     assert out["beta_only"]["median_max_rhat"] > 0.95
+
+
+def test_gpu_arm_control_flow_with_mocked_device(tmp_path):
+    """bench.py's own arm end to end on a box without a GPU (tests/wrapper/mock_bench.py: torch.cuda mocked, device
+    classes replaced by oracle-backed stand-ins): phases, counters, roofline arithmetic, the opt-in ESS leg and the JSON
+    line — which must be the only thing on stdout and carry every key of the driver's contract."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "wrapper", "mock_bench.py")], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert key in d, key
+    assert d["metric"] == "grad_evals_per_sec" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["steps"] == 2 and d["gpu_launches"] == 2 and d["n_gpus"] == 1 and d["scaling"] == "weak"
+    # 2 steps x 1 transition x 100 "gradients" in 2 x 5 ms of "device time" (the mock's counters)
+    assert abs(d["value"] - 2 * 100 * d["config"]["nuts_transitions_per_chain_per_step"] / 0.010) < 1e-6
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    D, N = 94, 10
+    assert rf["algorithmic_bytes_per_leapfrog"] == 56 * D + 4 * N and rf["algorithmic_bytes_per_gradient"] == 16 * D + 4 * N
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["unit"] == d["unit"]
+    assert d["ess"]["genes"] == 2 and d["ess"]["num_samples"] == 10 and "beta_only" in d["ess"]
+    assert "ESS leg done" in r.stderr and "e2e arm" in r.stderr
