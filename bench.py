@@ -135,7 +135,7 @@ def ess_leg(api, model, genes, G, n, chains=4, seed=11, ess_genes=64):
     s = api.Sampler(batch, api.nuts_cfg(n, n, chains, seed=seed)).run(chunk=50)
     seconds = s.total_ms * 1e-3
     status, _ = s.status()
-    ex = s.extract_small()
+    ex = s.extract_small(genes=np.arange(min(G, ess_genes)))
     bkeys = [k for k in ex if k.startswith("beta_level")]
     skeys = [k for k in ex if k not in bkeys and k not in ("diag", "n_draws")]
     ess_all, ess_beta, rhat_beta = [], [], []

@@ -455,14 +455,25 @@ class Sampler:
         return out
 
     # ---- constrained small block: what read_stan_csv would give for the non-spot variables ------
-    def extract_small(self):
+    def extract_small(self, genes=None, raw=None):
         """Per gene g: dict var -> array with the sample axis first, chains concatenated chain-major
-        (the order of `combined_<g>.csv`, bin/splotch:138-140).  beta_level_k: (S, L_k, C[, K])."""
+        (the order of `combined_<g>.csv`, bin/splotch:138-140).  beta_level_k: (S, L_k, C[, K]).
+        `genes`: indices of the genes wanted (default all; the first axis of every result then runs over them) and
+        `raw`: the triple of a previous `draws()` call — at 10^5 spots x K = 10 the non-spot block of a 512-gene batch
+        is tens of GB, so callers that walk over genes constrain a few at a time instead of the whole batch at once."""
         m = self.model
-        diag, small, nd = self.draws()
+        diag, small, nd = self.draws() if raw is None else raw
+        pm, ps = self.batch.beta_prior_mean, self.batch.beta_prior_std
+        G = self.G
+        if genes is not None:
+            genes = np.atleast_1d(np.asarray(genes, dtype=np.int64))
+            diag, small, nd = diag[genes], small[genes], nd[genes]
+            if pm is not None:
+                pm, ps = pm[genes], ps[genes]
+            G = len(genes)
         L1, L2, L3 = m.levels
         L, Cc, K = L1 + L2 + L3, m.C, m.K
-        G, nch, ns = self.G, self.nch, self.cfg.num_samples
+        nch, ns = self.nch, self.cfg.num_samples
         raw = small[..., : m.n_beta].reshape(G, nch * ns, L, Cc, K)
         sc = small[..., m.n_beta:].reshape(G, nch * ns, m.n_scalar)
         names = []
@@ -482,8 +493,8 @@ class Sampler:
             u = sc[..., i]
             out[nme] = (1.0 / (1.0 + np.exp(-u))) if nme in ("a", "theta") else np.exp(u) + (1e-6 if nme == "phi" else 0.0)
         if m.family == 1:
-            std = self.batch.beta_prior_std[:, None, None, None, :]
-            mean = self.batch.beta_prior_mean[:, None, None, None, :]
+            std = ps[:, None, None, None, :]
+            mean = pm[:, None, None, None, :]
             b1 = raw[:, :, :L1] * std + mean
         else:
             b1 = 2.0 * raw[:, :, :L1]

@@ -137,7 +137,8 @@ def batch_report(s, gene_ids, status, ess_genes=8):
     """One JSON-able dict per device batch (SURVEY.md §5 metrics: the reference only has CmdStan's progress lines):
     work done, sampler health, and bulk-ESS / split-R-hat of the betas and scalar parameters of the first genes."""
     from . import diagnostics as dg
-    diag, _, _ = s.draws()
+    raw = s.draws()
+    diag = raw[0]
     cnt = s.counters()
     nch, ns = s.nch, s.cfg.num_samples
     ok = (np.asarray(status) == 0).all(axis=1)
@@ -151,10 +152,11 @@ def batch_report(s, gene_ids, status, ess_genes=8):
                    treedepth_hist=np.bincount(d[:, 3].astype(int), minlength=11).tolist(),
                    mean_stepsize=float(d[:, 2].mean()), mean_accept_stat=float(d[:, 1].mean()))
     if ess_genes and ns >= 8 and ok.any():
-        ex = s.extract_small()
+        pick = np.nonzero(ok)[0][:ess_genes]
+        ex = s.extract_small(genes=pick, raw=raw)
         keys = [k for k in ex if k not in ("diag", "n_draws")]
         ess, rhat = [], []
-        for i in np.nonzero(ok)[0][:ess_genes]:
+        for i in range(len(pick)):
             cols = np.concatenate([ex[k][i].reshape(nch * ns, -1) for k in keys], axis=1).reshape(nch, ns, -1)
             e, r = dg.summarize(cols)
             ess.append(e)

@@ -103,8 +103,10 @@ def summarize(post: dict) -> dict:
 
 def summary_from_sampler(sampler, g: int) -> dict:
     """The same dictionary built from the on-device streaming summaries (no CSV round trip)."""
-    ex = sampler.extract_small() if not hasattr(sampler, "_ex_cache") else sampler._ex_cache
-    sampler._ex_cache = ex
+    # the raw draws of the batch are fetched once; each gene is constrained on its own (bounded host memory)
+    raw = sampler.draws() if not hasattr(sampler, "_raw_cache") else sampler._raw_cache
+    sampler._raw_cache = raw
+    ex = sampler.extract_small(genes=[g], raw=raw)
     sp = sampler.spot_summaries() if not hasattr(sampler, "_sp_cache") else sampler._sp_cache
     sampler._sp_cache = sp
     out = {}
@@ -113,7 +115,7 @@ def summary_from_sampler(sampler, g: int) -> dict:
             out[key] = {"mean": sp[key + "/mean"][g], "std": sp[key + "/std"][g]}
     for key in SUMMARY_VARS:
         if key in ex:
-            arr = ex[key][g]
+            arr = ex[key][0]
             if arr.ndim == 1:
                 arr = arr[:, None]
             d = {"mean": arr.mean(axis=0), "std": arr.std(axis=0)}

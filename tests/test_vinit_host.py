@@ -112,6 +112,23 @@ class _Sampler:
 
     extract_small = api.Sampler.extract_small
 
+    def spot_summaries(self, out=None):
+        """What the device accumulates while sampling: mean / std (ddof = 0, chains pooled) of log_lambda, exp(log_lambda)
+        and psi — here from write_array on the kept draws."""
+        m = self.model
+        cols = m.column_names()
+        i0 = cols.index("log_lambda.1")
+        res = {k: np.zeros((self.G, m.N)) for k in ("log_lambda/mean", "log_lambda/std", "lambda/mean", "lambda/std",
+                                                    "psi/mean", "psi/std")}
+        for g in range(self.G):
+            wa = self.batch.write_array(self._theta[g].reshape(-1, m.dim), gene_of=np.full(self.nch * self.cfg.num_samples, g))
+            ll = wa[:, i0:i0 + m.N]
+            for key, arr in (("log_lambda", ll), ("lambda", np.exp(ll)), ("psi", wa[:, :m.N])):
+                res[key + "/mean"][g], res[key + "/std"][g] = arr.mean(0), arr.std(0)
+        if not m.car:
+            res.pop("psi/mean"); res.pop("psi/std")
+        return res
+
 
 @pytest.fixture()
 def host_only(monkeypatch):
@@ -312,3 +329,33 @@ def stancsv_like(ex, g):
         for idx in np.ndindex(*a.shape[1:]):
             out[key + "." + ".".join(str(i + 1) for i in idx)] = a[(slice(None),) + idx]
     return out
+
+
+def test_summary_mode_equals_summary_of_the_csv(host_only, golden_dir, tmp_path):
+    """`-s` (summaries built per gene from the raw draws of the batch, no CSV) against `summarize(read_stan_csv(csv))` of
+    the same run: the dictionary splotch_summarize_output would have written (utils.py:234-257), gene by gene."""
+    data_dir = _c1_data_dir(golden_dir, tmp_path, (1, 2, 3))
+    common = ["-g", "1-3", "-d", data_dir, "-b", "comp_splotch_stan_model", "-n", "15", "-c", "2", "--seed", "8"]
+    assert cli.main(common + ["-o", str(tmp_path / "csv")]) == 0
+    assert cli.main(common + ["-o", str(tmp_path / "sum"), "-s"]) == 0
+    for g in (1, 2, 3):
+        post = stancsv.read_stan_csv(os.path.join(str(tmp_path / "csv"), "0", "combined_%d.csv" % g), stancsv.SUMMARY_VARS)
+        want = stancsv.summarize(post)
+        got = stancsv.read_summary(os.path.join(str(tmp_path / "sum"), "0", "combined_%d.hdf5" % g))
+        assert set(got) == set(want)
+        for key in want:
+            for stat in want[key]:
+                assert got[key][stat].shape == want[key][stat].shape, (key, stat)
+                assert np.allclose(got[key][stat], want[key][stat], rtol=1e-10, atol=1e-12), (g, key, stat)
+
+
+def test_extract_small_of_selected_genes(host_only, golden_dir):
+    datas = [rdump.read_rdump(os.path.join(golden_dir, "c1", "data_%d.R" % g)) for g in (1, 2, 3, 4)]
+    shared = {k: v for k, v in datas[0].items() if k not in rdump.GENE_KEYS}
+    model = api.Model(shared, "comp_splotch_stan_model")
+    batch = api.Batch(model, *[np.stack([d[k] for d in datas]) for k in rdump.GENE_KEYS])
+    s = api.Sampler(batch, api.nuts_cfg(5, 6, 2, seed=1)).run()
+    full = s.extract_small()
+    part = s.extract_small(genes=[3, 1], raw=s.draws())
+    for key in full:
+        assert np.array_equal(part[key], full[key][[3, 1]]), key
