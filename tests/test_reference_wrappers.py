@@ -78,3 +78,20 @@ def test_a_failing_binary_fails_the_wrapper(golden_dir, tmp_path):
     r = subprocess.run(["bash", os.path.join(ROOT, "tests", "wrapper", "run_wrapper.sh"), "plain", "4", data, out, binary,
                         "5", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "Error reading data file" in r.stderr
+
+
+def test_unmodified_wrapper_in_summary_mode(golden_dir, tmp_path):
+    """`splotch … -s` (bin/splotch:145-151): the wrapper calls `splotch_summarize_output -p CSV -o HDF5` from PATH and
+    removes the CSV; with this repo's bin/ on PATH the summary holds the groups summarize_stan_hdf5 writes."""
+    if not os.path.exists(os.path.join(REF_BIN, "splotch")):
+        pytest.skip("/root/reference not on this box")
+    data, out, binary = _setup(golden_dir, tmp_path, 2)
+    env = dict(os.environ, PATH=os.path.join(ROOT, "bin") + os.pathsep + os.environ["PATH"])
+    r = subprocess.run(["bash", os.path.join(REF_BIN, "splotch"), "-g", "2", "-d", data, "-o", out, "-b", binary, "-n", "9",
+                        "-c", "2", "-s"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert not os.path.exists(os.path.join(out, "0", "combined_2.csv"))                  # removed by the wrapper
+    got = stancsv.read_summary(os.path.join(out, "0", "combined_2.hdf5"))
+    assert set(got) == {"log_lambda", "lambda", "beta_level_1", "psi", "sigma", "theta", "tau", "a"}
+    assert got["beta_level_1"]["samples"].shape == (18, 1, 14, 5) and got["lambda"]["mean"].shape == (10,)
+    assert got["sigma"]["mean"].shape == (1,) and set(got["psi"]) == {"mean", "std"}
