@@ -109,18 +109,20 @@ def grid_chunk_eigs(h: int, w: int, chunk: int = 100) -> np.ndarray:
 
 
 def scale_and_round(mat: np.ndarray) -> np.ndarray:
-    """Composition rounding of the reference (utils.py:672-682, 729-731)."""
-    x = np.round(mat, 8)
-    x[:, -1] = 1 - x[:, :-1].sum(axis=1)
-    x = np.maximum(x, 0)
-    x = x / x.sum(axis=1)[:, None]
-    x = np.around(x, decimals=5)
-    for i in range(x.shape[0]):
-        im = int(np.argmax(x[i]))
-        others = np.delete(np.arange(x.shape[1]), im)
-        x[i, im] = 1.0 - np.sum(x[i, others])
-    assert x.min() >= 0.0
-    return x
+    """Cell-type fractions as `generate_dictionary` stores them (/root/reference/splotch/utils.py:672-682, 729-731):
+    8-decimal rounding with the last column closing the simplex, clipping at 0 and renormalising, 5-decimal rounding,
+    and finally the largest entry of every spot absorbing what is missing from 1.  All rows at once."""
+    frac = np.round(np.asarray(mat, dtype=np.float64), 8)
+    frac[:, -1] = 1 - frac[:, :-1].sum(axis=1)
+    frac = np.clip(frac, 0.0, None)
+    frac = np.around(frac / frac.sum(axis=1, keepdims=True), decimals=5)
+    rows = np.arange(frac.shape[0])
+    top = frac.argmax(axis=1)
+    rest = frac.copy()
+    rest[rows, top] = 0.0
+    frac[rows, top] = 1.0 - rest.sum(axis=1)
+    assert frac.min() >= 0.0
+    return frac
 
 
 # ----------------------------------------------------------------------------

@@ -96,3 +96,19 @@ def test_reference_rdump_reader_on_our_writer(ref_utils, golden_dir, tmp_path):
     for k in d:
         assert np.array_equal(np.asarray(theirs[k]), np.asarray(d[k])), k
     assert open(p).read() == open(os.path.join(golden_dir, "c1", "data_3.R")).read()      # byte-identical files
+
+
+def test_composition_rounding_matches_the_reference(ref_utils):
+    """synth.scale_and_round (all rows at once) against the reference's row loop (utils.py:672-682 after :729-730)."""
+    from csplotch_b200 import synth
+    rng = np.random.default_rng(0)
+    for K in (1, 2, 5, 8, 10, 16):
+        raw = rng.dirichlet(np.full(K, 0.3), size=500)
+        raw[::50] = np.eye(K)[rng.integers(0, K, 10)]                   # pure spots
+        want = np.round(raw, 8)
+        want[:, -1] = 1 - want[:, :-1].sum(axis=1)
+        want = ref_utils.scale_and_round(want)
+        got = synth.scale_and_round(raw)
+        assert np.abs(got - want).max() <= 5e-16 and np.abs(got.sum(axis=1) - 1).max() < 1e-15
+        if K < 8:                      # numpy sums 8 or more terms in a different order along an axis than over a row
+            assert np.array_equal(got, want)
