@@ -112,3 +112,29 @@ def test_composition_rounding_matches_the_reference(ref_utils):
         assert np.abs(got - want).max() <= 5e-16 and np.abs(got.sum(axis=1) - 1).max() < 1e-15
         if K < 8:                      # numpy sums 8 or more terms in a different order along an axis than over a row
             assert np.array_equal(got, want)
+
+
+def test_car_helpers_match_the_reference(ref_utils, tmp_path, monkeypatch):
+    """The inputs of the synthetic configs are built the way the reference builds them: 4-neighbour adjacency
+    (utils.py:530-552), symmetric CSR `U`, `V` (utils.py:592-614) and the chunked eigenvalues of Visium-HD sized
+    tissues (utils.py:629-670)."""
+    from csplotch_b200 import synth
+    monkeypatch.setattr(synth, "_DATA", str(tmp_path))                           # keep the eigenvalue cache out of the tree
+    for h, w in ((7, 5), (12, 23)):
+        coords = np.array([(i, j) for i in range(h) for j in range(w)])          # row-major, as synth numbers the bins
+        W = ref_utils.get_spot_adjacency_matrix_4n(coords).toarray()
+        pairs = synth.grid4_pairs(h, w)
+        mine = np.zeros_like(W)
+        mine[pairs[:, 0], pairs[:, 1]] = 1
+        mine[pairs[:, 1], pairs[:, 0]] = 1
+        assert np.array_equal(mine, W)
+        V, U = synth.pairs_to_csr(pairs, h * w)
+        Vr, Ur = ref_utils.sparse_to_csr_indptr(pairs + 1, h * w)
+        assert np.array_equal(V, Vr) and np.array_equal(U, Ur)
+    # chunk side 10 <-> chunksize 100 spots; sizes whose largest coordinate is not a multiple of the chunk side (the
+    # reference's loop would drop the last row / column there and trip its own assertion)
+    for h, w in ((23, 17), (32, 26)):
+        coords_str = np.array(["%d_%d" % (i, j) for i in range(h) for j in range(w)])
+        want = ref_utils.eigs_square_chunking(coords_str, chunksize=100)
+        got = synth.grid_chunk_eigs(h, w, chunk=10)
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-12
