@@ -138,3 +138,19 @@ def test_car_helpers_match_the_reference(ref_utils, tmp_path, monkeypatch):
         want = ref_utils.eigs_square_chunking(coords_str, chunksize=100)
         got = synth.grid_chunk_eigs(h, w, chunk=10)
         assert got.shape == want.shape and np.abs(got - want).max() < 1e-12
+
+
+def test_visium_hex_adjacency_matches_the_reference(ref_utils):
+    """synth.hex_pairs (odd-r offsets) against the reference's rule for Visium arrays: true-hex coordinates and
+    distance <= 1.2 (utils_visium.py:80-87, 214-217 -> utils.py:511-528), on a 12 x 9 array in pseudo-hex indexing."""
+    import importlib
+    from csplotch_b200 import synth
+    ref_utils_visium = importlib.import_module("splotch.utils_visium")
+    rows, cols = 12, 9
+    pseudo = [(2 * x + (y % 2), y) for y in range(rows) for x in range(cols)]      # Visium's doubled-x, odd rows offset
+    W = np.asarray(ref_utils_visium.get_spot_adjacency_matrix_hex(pseudo))
+    pairs = synth.hex_pairs(rows, cols)
+    mine = np.zeros_like(W)
+    mine[pairs[:, 0], pairs[:, 1]] = 1
+    mine[pairs[:, 1], pairs[:, 0]] = 1
+    assert np.array_equal(mine, W) and W.sum(axis=1).max() == 6
