@@ -154,3 +154,40 @@ def test_visium_hex_adjacency_matches_the_reference(ref_utils):
     mine[pairs[:, 0], pairs[:, 1]] = 1
     mine[pairs[:, 1], pairs[:, 0]] = 1
     assert np.array_equal(mine, W) and W.sum(axis=1).max() == 6
+
+
+def test_build_shared_equals_generate_dictionary(ref_utils):
+    """The gene-shared dictionary of the synthetic configs (synth.build_shared) key by key against the reference's
+    generate_dictionary (utils.py:684-774) on the same small Visium-like design: compositional, 3 levels, CAR + ZI."""
+    from scipy.sparse import csr_matrix
+    from csplotch_b200 import synth
+    rng = np.random.default_rng(3)
+    shapes = [(5, 4), (3, 6), (4, 4)]
+    C, K = 4, 3
+    levels, l2, l3 = (2, 3, 3), [1, 2, 2], [1, 2, 3]
+    tm = [1, 3, 2]
+    sizes, pairs, eigs, W_list, Wn, coords, sf, aar, comp = [], [], [], [], [], [], [], [], []
+    for (h, w) in shapes:
+        n = h * w
+        p = synth.hex_pairs(h, w)
+        W = np.zeros((n, n))
+        W[p[:, 0], p[:, 1]] = W[p[:, 1], p[:, 0]] = 1
+        sizes.append(n); pairs.append(p); eigs.append(synth.car_eigenvalues(p, n))
+        W_list.append(csr_matrix(W)); Wn.append(len(p))
+        coords.append(np.array(["%d_%d" % (x, y) for y in range(h) for x in range(w)]))
+        sf.append(rng.uniform(0.2, 3.0, n))
+        d = rng.integers(0, C, n)
+        aar.append(np.eye(C, dtype=int)[d].T)                               # (C, n) one-hot, as the annotation files
+        comp.append(rng.dirichlet(np.full(K, 0.5), n).T)                    # (K, n)
+    D = np.concatenate([a.argmax(0) + 1 for a in aar])
+    E = np.vstack([c.T for c in comp])
+    mine = synth.build_shared(sizes, pairs, eigs, D, tm, levels, l2, l3, np.concatenate(sf), C, zi=1, car=1,
+                              E=synth.scale_and_round(E))
+    ref = ref_utils.generate_dictionary(sizes, len(sizes), C, list(levels), coords, sf, aar, [l2, l3], tm, W_list, Wn,
+                                        True, True, False, True, comp)
+    assert set(ref) <= set(mine) | {"N_celltypes"}
+    for key in ref:
+        a, b = np.asarray(ref[key], dtype=np.float64), np.asarray(mine[key], dtype=np.float64)
+        assert a.shape == b.shape or a.size == b.size == 0, key
+        if a.size:
+            assert np.allclose(a, b, rtol=0, atol=1e-12 if key in ("eig_values", "E") else 0), key
