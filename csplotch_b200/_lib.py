@@ -47,11 +47,11 @@ class Dims(C.Structure):
 SYMBOLS = [
     "csplotch_last_error", "csplotch_abi_version", "csplotch_device_count", "csplotch_set_device",
     "csplotch_model_create", "csplotch_model_destroy", "csplotch_model_dims",
-    "csplotch_batch_create", "csplotch_batch_create_dev", "csplotch_batch_destroy",
-    "csplotch_log_prob_grad", "csplotch_log_prob_grad_dev", "csplotch_write_array", "csplotch_leapfrog_fixed",
+    "csplotch_batch_create", "csplotch_batch_create_dev", "csplotch_batch_destroy", "csplotch_batch_set_gene_ids",
+    "csplotch_log_prob_grad", "csplotch_log_prob_grad_dev", "csplotch_write_array", "csplotch_leapfrog_fixed", "csplotch_leapfrog_bench",
     "csplotch_nuts_cfg_default", "csplotch_sampler_create", "csplotch_sampler_destroy", "csplotch_sampler_init",
     "csplotch_sampler_advance", "csplotch_sampler_sync", "csplotch_sampler_last_ms", "csplotch_sampler_counters",
-    "csplotch_sampler_status", "csplotch_sampler_profile", "csplotch_sampler_get_draws", "csplotch_sampler_get_theta_draws",
+    "csplotch_sampler_status", "csplotch_sampler_slot_ns", "csplotch_sampler_profile", "csplotch_sampler_get_draws", "csplotch_sampler_get_theta_draws",
     "csplotch_sampler_get_state", "csplotch_sampler_get_spot_summaries", "csplotch_rdump_read_genes", "csplotch_host_alloc", "csplotch_host_free",
     "csplotch_csv_write",
 ]

@@ -266,7 +266,10 @@ def unconstrain(model: "Model", init: dict, radius: float = 2.0, seed: int = 0) 
 class Batch:
     """counts (+ beta priors) of G genes on the GPU.  counts: (G, N) int; priors: (G, K) for comp."""
 
-    def __init__(self, model: Model, counts, beta_prior_mean=None, beta_prior_std=None, gene_id0: int = 0):
+    def __init__(self, model: Model, counts, beta_prior_mean=None, beta_prior_std=None, gene_id0: int = 0,
+                 gene_ids=None):
+        """`gene_ids` (length G) gives every gene of the batch its own id instead of gene_id0 + g: the id keys the
+        RNG stream, so a gene list can be handed over in any order (cost-sorted, dealt over ranks: shard.deal)."""
         self.model = model
         self.lib = model.lib
         c = np.ascontiguousarray(np.asarray(counts, dtype=np.int32).reshape(-1, model.N))
@@ -284,6 +287,13 @@ class Batch:
                                              C.c_uint32(gene_id0), C.byref(h)))
         self.h = h
         self.gene_id0 = gene_id0
+        self.gene_ids = np.arange(self.G, dtype=np.uint32) + np.uint32(gene_id0)
+        if gene_ids is not None:
+            ids = np.ascontiguousarray(np.asarray(gene_ids, dtype=np.uint32).reshape(-1))
+            if ids.size != self.G:
+                raise CsplotchError("gene_ids must have one entry per gene")
+            check(self.lib.csplotch_batch_set_gene_ids(self.h, _p(ids)))
+            self.gene_ids = ids
 
     def close(self):
         if getattr(self, "h", None):
@@ -330,6 +340,13 @@ class Batch:
                                                C.c_int32(B), C.c_double(eps), C.c_int32(n_steps), _p(tho), _p(po),
                                                _p(H)))
         return tho, po, H
+
+    def leapfrog_bench(self, B, eps=1e-4, n_steps=8, reps=3):
+        """Diagnostic: average device milliseconds of one launch of B fixed-step trajectories (csplotch_leapfrog_bench)."""
+        ms = C.c_float()
+        check(self.lib.csplotch_leapfrog_bench(self.h, C.c_int32(B), C.c_double(eps), C.c_int32(n_steps), C.c_int32(reps),
+                                               C.byref(ms)))
+        return float(ms.value)
 
 
 def nuts_cfg(num_warmup, num_samples, num_chains=4, seed=0, keep_draws=False, **kw) -> NutsCfg:
@@ -403,6 +420,15 @@ class Sampler:
         check(self.lib.csplotch_sampler_profile(self.h, out))
         keys = ["cyc_eval", "cyc_merge", "cyc_copy", "cyc_other", "n_merge", "n_copy", "cyc_pro", "cyc_fin"]
         return dict(zip(keys, [int(x) for x in out]))
+
+    def launch_tail(self):
+        """Diagnostic: (mean, max) busy seconds over the resident CTAs of the last launch; 1 - mean / max is the
+        fraction of the launch the average SM slot spent idle waiting for the longest chain."""
+        n = C.c_int32()
+        check(self.lib.csplotch_sampler_slot_ns(self.h, None, C.c_int32(0), C.byref(n)))
+        ns = np.zeros(n.value, dtype=np.int64)
+        check(self.lib.csplotch_sampler_slot_ns(self.h, _p(ns), C.c_int32(n.value), C.byref(n)))
+        return float(ns.mean()) * 1e-9, float(ns.max()) * 1e-9
 
     def status(self):
         st = np.zeros((self.G, self.nch), dtype=np.int32)

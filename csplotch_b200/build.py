@@ -38,12 +38,12 @@ def is_stale() -> bool:
 DEV_OUT = os.path.join(HERE, "libcsplotch_b200_dev.so")
 
 
-def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
-    """dev=True: K in {1, 10} only, written to libcsplotch_b200_dev.so (experiments; load it with
-    CSPLOTCH_LIB=<path>); the product library always holds every instantiation."""
+def build(force: bool = False, verbose: bool = False, dev: bool = False, out: str | None = None) -> str:
+    """dev=True: K in {1, 10} only, written to libcsplotch_b200_dev.so (or `out`; experiments: load it with
+    CSPLOTCH_LIB=<path>, extra -D flags from CSPLOTCH_DEV_DEFS); the product library always holds every instantiation."""
     if not dev and not force and not is_stale():
         return OUT
-    out = DEV_OUT if dev else OUT
+    out = (out or DEV_OUT) if dev else OUT
     cmd = ([nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DCSPLOTCH_DEV_KT"] + os.environ.get("CSPLOTCH_DEV_DEFS", "").split() if dev else [])
            + ["-o", out, SRC, HOST_SRC])
     subprocess.check_call(cmd)
@@ -51,4 +51,5 @@ def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, dev="--dev" in sys.argv))
+    _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, dev="--dev" in sys.argv, out=_out))

@@ -82,6 +82,7 @@ struct csplotch_batch {
   DevBuf buf;
   int G = 0;
   uint32_t gene_id0 = 0;
+  uint32_t *gene_ids = nullptr;  // [G] device: the id that keys the RNG stream of every gene (gene_id0 + g unless given)
   int *counts = nullptr;     // [G][Nc] internal spot order
   double *pm = nullptr;      // [G][K]
   double *ps = nullptr;
@@ -97,7 +98,9 @@ struct SamplerDev {
   int *queue;
   int W, num_chains, n_slots, have_init;
   int pool_vecs;                    // 3 * max_depth + 8 D-vectors of momenta / rho sums per slot
-  uint32_t gene_id0;
+  const uint32_t *gene_ids;         // [G]
+  const int *order;                 // [W] gene-chains in the order the queue hands them out (longest first)
+  long long *slot_ns;               // [n_slots] nanoseconds from a CTA's start to its exit in the last launch (launch tail)
   NutsConfig cfg;
   const int *counts;
   const double *pm, *ps, *lgam, *nnz;
@@ -113,6 +116,10 @@ struct csplotch_sampler {
   bool timed = false;
   int grid = 0;
   int64_t launches = 0;
+  int *order_dev = nullptr;          // [W] queue order of the next launch
+  std::vector<double> nnz_host;      // [G] non-zero counts per gene: the cost estimate before the first transition
+  std::vector<ChainScalars> cs_host;
+  std::vector<int> order_host;
   ~csplotch_sampler() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -230,7 +237,7 @@ __device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, do
   if (m.tiled) {
     if (threadIdx.x == 0) {
       for (int i = 0; i < 6; ++i) mbar_init(ops.mbar + i, 1);
-      for (int i = 6; i < 10; ++i) mbar_init(ops.mbar + i, kBlock);
+      for (int i = 6; i < 10; ++i) mbar_init(ops.mbar + i, kArriveCount);
       mbar_fence_init();
       ops.ring[ring_tiles * kTile] = 0.0;
       ops.ring[ring_tiles * kTile + 1] = 0.0;
@@ -320,6 +327,8 @@ __global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
 k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ SamplerDev s, int n_iter) {
   __shared__ int s_work;
   const size_t Di = m_in.Di;
+  long long t_start_ns = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
   double *ws = s.ws + (size_t)blockIdx.x * (size_t)(s.pool_vecs + 6) * Di;
   // the model descriptor is read all over the per-evaluation prologue / epilogue: a shared-memory copy turns
   // those dependent generic loads from the parameter bank into LDS
@@ -330,18 +339,21 @@ k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ Sa
   bind_smem(ops, m, smem_d);
   ops.jacobian = 1;
   for (;;) {
-    if (threadIdx.x == 0) s_work = atomicAdd(s.queue, 1);
+    if (threadIdx.x == 0) {
+      const int t = atomicAdd(s.queue, 1);
+      s_work = t < s.W ? s.order[t] : -1;
+    }
     __syncthreads();
     const int w = s_work;
     __syncthreads();
-    if (w >= s.W) break;
+    if (w < 0) break;
     const int g = w / s.num_chains, c = w - g * s.num_chains;
     ops.gn.counts = s.counts + (size_t)g * m.Nc;
     ops.gn.pm = s.pm ? s.pm + (size_t)g * m.K : nullptr;
     ops.gn.ps = s.ps ? s.ps + (size_t)g * m.K : nullptr;
     ops.gn.lgam = s.lgam[g];
     ops.gn.nnz = s.nnz[g];
-    ops.key = RngKey{s.cfg.seed, (uint32_t)c + 1u, s.gene_id0 + (uint32_t)g};
+    ops.key = RngKey{s.cfg.seed, (uint32_t)c + 1u, s.gene_ids[g]};
     ops.pool = ws;
     ops.zq[0] = ws + (size_t)s.pool_vecs * Di;
     ops.zg[0] = ops.zq[0] + Di;
@@ -375,6 +387,11 @@ k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ Sa
 #endif
       s.cs[w] = cs;
     }
+  }
+  if (threadIdx.x == 0) {
+    long long t_end_ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
+    s.slot_ns[blockIdx.x] = t_end_ns - t_start_ns;
   }
 }
 
@@ -740,6 +757,11 @@ static int batch_finish(csplotch_model *m, csplotch_batch *b, const int *counts_
   CU_TRY(b->buf.alloc(&b->counts, (size_t)b->G * dm.Nc));
   CU_TRY(b->buf.alloc(&b->lgam, (size_t)b->G));
   CU_TRY(b->buf.alloc(&b->nnz, (size_t)b->G));
+  {
+    std::vector<uint32_t> ids((size_t)b->G);
+    for (int g = 0; g < b->G; ++g) ids[g] = b->gene_id0 + (uint32_t)g;
+    CU_TRY(b->buf.upload(&b->gene_ids, ids));
+  }
   k_repack_counts<<<1184, 256, 0, st>>>(counts_raw_dev, b->counts, perm_dev, b->G, dm.N, dm.Nc);
   k_gene_consts<<<std::min(b->G, 1184), kBlock, 0, st>>>(b->counts, b->G, dm.N, dm.Nc, b->lgam, b->nnz);
   CU_TRY(cudaGetLastError());
@@ -787,6 +809,14 @@ extern "C" int32_t csplotch_batch_create(csplotch_model *m, const int32_t *count
 }
 
 extern "C" void csplotch_batch_destroy(csplotch_batch *b) { delete b; }
+
+// The RNG stream of a gene is keyed by its id, so a gene list may be handed over in ANY order (cost-sorted,
+// dealt round-robin over ranks) without changing a single draw.
+extern "C" int32_t csplotch_batch_set_gene_ids(csplotch_batch *b, const uint32_t *gene_ids) {
+  if (!b || !gene_ids) return fail(CSPLOTCH_E_INVALID, "null argument");
+  CU_TRY(cudaMemcpy(b->gene_ids, gene_ids, (size_t)b->G * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return CSPLOTCH_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // host: launch helpers
@@ -939,6 +969,61 @@ extern "C" int32_t csplotch_leapfrog_fixed(csplotch_batch *b, const double *thet
   return CSPLOTCH_OK;
 }
 
+// Device-timed microbenchmark of the fused leapfrog (diagnostic: scripts/leap_bench.py, profiles/): Bn trajectories
+// of n_steps fixed-size steps from deterministic pseudo-random states, `reps` timed launches after one warm-up;
+// nothing crosses PCIe.  Work per launch = Bn * (1 gradient + n_steps leapfrogs).
+__global__ void k_fill_hash(double *v, size_t n, const int *__restrict__ imap, int Di, uint32_t salt, double scale, double base) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + salt;
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    const bool live = imap[i % (size_t)Di] >= 0;
+    v[i] = live ? base + scale * ((double)h * (1.0 / 4294967296.0) - 0.5) : (base != 0.0 ? 1.0 : 0.0);
+  }
+}
+extern "C" int32_t csplotch_leapfrog_bench(csplotch_batch *b, int32_t Bn, double eps, int32_t n_steps, int32_t reps,
+                                           float *ms_avg) {
+  if (!b || Bn < 1 || n_steps < 0 || reps < 1 || !ms_avg) return fail(CSPLOTCH_E_INVALID, "bad argument");
+  csplotch_model *m = b->m;
+  const DevModel &dm = m->dm;
+  DevBuf tmp;
+  double *q = nullptr, *p = nullptr, *g = nullptr, *mi = nullptr, *H = nullptr;
+  const size_t nI = (size_t)Bn * dm.Di;
+  CU_TRY(tmp.alloc(&q, nI));
+  CU_TRY(tmp.alloc(&p, nI));
+  CU_TRY(tmp.alloc(&g, nI));
+  CU_TRY(tmp.alloc(&mi, nI));
+  CU_TRY(tmp.alloc(&H, (size_t)Bn));
+  const int nb = sm_count() * 8;
+  k_fill_hash<<<nb, 256>>>(q, nI, dm.imap, dm.Di, 1u, 1.0, 0.0);
+  k_fill_hash<<<nb, 256>>>(p, nI, dm.imap, dm.Di, 2u, 2.0, 0.0);
+  k_fill_hash<<<nb, 256>>>(mi, nI, dm.imap, dm.Di, 3u, 0.5, 1.0);
+  CU_TRY(cudaMemset(g, 0, nI * sizeof(double)));
+  const int grid = std::min(Bn, sm_count() * ctas_per_sm(m->kt));
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  cudaError_t e = cudaSuccess;
+  for (int r = 0; r <= reps && e == cudaSuccess; ++r) {
+    if (r == 1) cudaEventRecord(e0);
+    DISPATCH_KT(m->kt, {
+      e = set_smem(k_leapfrog_fixed<KT>, m->smem_bytes);
+      if (e == cudaSuccess)
+        k_leapfrog_fixed<KT><<<grid, kBlock, m->smem_bytes>>>(dm, b->counts, b->pm, b->ps, b->lgam, b->nnz, b->G, q, p, g,
+                                                             mi, nullptr, Bn, eps, n_steps, H);
+    });
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  cudaEventRecord(e1);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (e != cudaSuccess) return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e));
+  *ms_avg = ms / (float)reps;
+  return CSPLOTCH_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host: sampler
 // ------------------------------------------------------------------------------------------------
@@ -961,7 +1046,7 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   SamplerDev &sd = s->sd;
   memset(&sd, 0, sizeof(sd));
   const int W = b->G * cfg->num_chains;
-  sd.W = W; sd.num_chains = cfg->num_chains; sd.gene_id0 = b->gene_id0;
+  sd.W = W; sd.num_chains = cfg->num_chains; sd.gene_ids = b->gene_ids;
   sd.cfg = NutsConfig{cfg->num_warmup, cfg->num_samples, cfg->max_depth, cfg->delta, cfg->gamma, cfg->kappa, cfg->t0,
                       cfg->init_buffer, cfg->term_buffer, cfg->window, cfg->init_radius, cfg->stepsize, cfg->seed};
   sd.counts = b->counts; sd.pm = b->pm; sd.ps = b->ps; sd.lgam = b->lgam; sd.nnz = b->nnz;
@@ -998,6 +1083,9 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   A(&sd.summ, (size_t)W * 6 * dm.N);
   if (cfg->keep_draws) A(&sd.theta, (size_t)W * ns * dm.D);
   A(&sd.queue, 1);
+  A(&s->order_dev, (size_t)W);
+  sd.order = s->order_dev;
+  A(&sd.slot_ns, (size_t)sd.n_slots);
   if (e != cudaSuccess) {
     delete s;
     return fail(e == cudaErrorMemoryAllocation ? CSPLOTCH_E_NOMEM : CSPLOTCH_E_CUDA,
@@ -1013,11 +1101,38 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   CU_TRY(cudaMemsetAsync(sd.diag, 0, (size_t)W * ns * 7 * sizeof(double), s->stream));
   CU_TRY(cudaMemsetAsync(sd.small, 0, (size_t)W * ns * dm.nsmall_true * sizeof(double), s->stream));
   CU_TRY(cudaStreamSynchronize(s->stream));
+  s->nnz_host.resize((size_t)b->G);
+  CU_TRY(cudaMemcpy(s->nnz_host.data(), b->nnz, (size_t)b->G * sizeof(double), cudaMemcpyDeviceToHost));
   *out = s;
   return CSPLOTCH_OK;
 }
 
 extern "C" void csplotch_sampler_destroy(csplotch_sampler *s) { delete s; }
+
+// Queue order of the next launch: longest expected gene-chain first (LPT), so that the deepest trees start at the
+// beginning of the launch instead of bounding its tail.  Expected cost = n_leapfrog__ of the chain's most recent
+// transition (the tree depth follows the adapted step size, so it persists), or, before the first transition, the
+// number of non-zero counts of the gene.  The order never changes a result: every random number is keyed by
+// (seed, gene id, chain, iteration, purpose).  CSPLOTCH_QUEUE_ORDER=index restores index order (A/B measurements).
+static int build_order(csplotch_sampler *s) {
+  const int W = s->sd.W, nch = s->sd.num_chains;
+  s->order_host.resize((size_t)W);
+  for (int w = 0; w < W; ++w) s->order_host[w] = w;
+  const char *mode = std::getenv("CSPLOTCH_QUEUE_ORDER");
+  if (!(mode && std::string(mode) == "index")) {
+    s->cs_host.resize((size_t)W);
+    CU_TRY(cudaMemcpyAsync(s->cs_host.data(), s->sd.cs, (size_t)W * sizeof(ChainScalars), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    std::vector<double> cost((size_t)W);
+    for (int w = 0; w < W; ++w) {
+      const ChainScalars &c = s->cs_host[w];
+      cost[w] = (c.initialized && c.iter > 0) ? 1e9 + (double)c.last_nleap : s->nnz_host[w / nch];
+    }
+    std::stable_sort(s->order_host.begin(), s->order_host.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  }
+  CU_TRY(cudaMemcpyAsync(s->order_dev, s->order_host.data(), (size_t)W * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+  return CSPLOTCH_OK;
+}
 
 extern "C" int32_t csplotch_sampler_init(csplotch_sampler *s, const double *theta_init) {
   if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
@@ -1038,6 +1153,10 @@ extern "C" int32_t csplotch_sampler_init(csplotch_sampler *s, const double *thet
 extern "C" int32_t csplotch_sampler_advance(csplotch_sampler *s, int32_t n_iter, int32_t sync) {
   if (!s || n_iter < 0) return fail(CSPLOTCH_E_INVALID, "bad argument");
   csplotch_model *m = s->b->m;
+  {
+    const int rc = build_order(s);
+    if (rc) return rc;
+  }
   CU_TRY(cudaMemsetAsync(s->sd.queue, 0, sizeof(int), s->stream));
   CU_TRY(cudaEventRecord(s->ev0, s->stream));
   cudaError_t e = cudaSuccess;
@@ -1098,6 +1217,18 @@ extern "C" int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out8) 
   for (auto &x : h) {
     out8[0] += x.cyc_eval; out8[1] += x.cyc_merge; out8[2] += x.cyc_copy; out8[3] += x.cyc_other;
     out8[4] += x.n_merge; out8[5] += x.n_copy; out8[6] += x.cyc_pro; out8[7] += x.cyc_fin;
+  }
+  return CSPLOTCH_OK;
+}
+
+// busy time of every resident CTA in the last launch: the spread between the mean and the maximum is the launch tail
+extern "C" int32_t csplotch_sampler_slot_ns(csplotch_sampler *s, int64_t *ns, int32_t cap, int32_t *n_slots) {
+  if (!s || !n_slots) return fail(CSPLOTCH_E_INVALID, "null argument");
+  *n_slots = s->sd.n_slots;
+  if (ns) {
+    if (cap < s->sd.n_slots) return fail(CSPLOTCH_E_INVALID, "buffer too small");
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    CU_TRY(cudaMemcpy(ns, s->sd.slot_ns, (size_t)s->sd.n_slots * sizeof(long long), cudaMemcpyDeviceToHost));
   }
   return CSPLOTCH_OK;
 }

@@ -191,9 +191,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+#ifdef CSP_WAIT_HINT
   // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~the hint
   // elapses) instead of burning issue slots of the other CTA on the SM in a polling loop
-  uint32_t ok;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -201,7 +202,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
   } while (!ok);
+#else
+  // plain try_wait (hardware-default suspend window) in a loop
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+#endif
 }
+// CTA-wide "everyone has done X" barriers: one arrival per WARP (lane 0 after __syncwarp, which orders the
+// warp's shared-memory accesses before the release-arrive) unless CSP_ARRIVE_ALL restores one per thread
+#ifdef CSP_ARRIVE_ALL
+constexpr uint32_t kArriveCount = 256;
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar) { mbar_arrive(bar); }
+#else
+constexpr uint32_t kArriveCount = 8;
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+#endif
 
 // E[j][k] in the tile-major layout [NT][K][kTile]
 __device__ __forceinline__ const double *E_ptr(const DevModel &m, int j) {
@@ -650,7 +673,7 @@ struct DevOps {
     double qn = d[t];
     if (LEAP) qn += eps * d[3 * kTile + t] * (d[kTile + t] - 0.5 * eps * d[2 * kTile + t]);
     smem_d[c.ring_o + ((k * kTile + t) & RMASK)] = qn;
-    mbar_arrive(c.mbar + 6 + (seq & 1u));  // "psi of tile k is in the ring" (256 arrivals per use)
+    mbar_arrive_cta(c.mbar + 6 + (seq & 1u));  // "psi of tile k is in the ring"
   }
 
   // per-tile contribution of one warp to the bottom-level bins: G[bin][k] += sum_lanes gj * E[lane][k]
@@ -926,7 +949,7 @@ struct DevOps {
         }
       }
       PWMARK(w_post);
-      mbar_arrive(c.mbar + 8 + (seq & 1u));  // this thread no longer reads the staged inputs of tile k
+      mbar_arrive_cta(c.mbar + 8 + (seq & 1u));  // this warp no longer reads the staged inputs of tile k
 #pragma unroll
       for (int i = 0; i < KP; ++i) e[i] *= gj;
       PW(w_bins, add_bins<KP>(c.bins_o, e, bin));

@@ -48,7 +48,8 @@ struct ChainScalars {
   double eps;
   double da_mu, da_counter, da_sbar, da_xbar;
   uint32_t wa_num_warmup, wa_init_buffer, wa_term_buffer, wa_base_window;
-  uint32_t wa_counter, wa_size, wa_next, pad_;
+  uint32_t wa_counter, wa_size, wa_next;
+  uint32_t last_nleap;  // n_leapfrog__ of the most recent transition: the cost estimate that orders the work queue
   double wel_n;
   long long n_leapfrog_total;  // sum of n_leapfrog__ over transitions
   long long n_grad_total;      // every gradient evaluation actually performed
@@ -229,6 +230,7 @@ struct Nuts {
     info.stepsize = cs.eps;
     cs.n_leapfrog_total += n_leapfrog;
     cs.n_grad_total += n_leapfrog;
+    cs.last_nleap = (uint32_t)n_leapfrog;
   }
 
   // ---- base_hmc::init_stepsize ----------------------------------------------------------------

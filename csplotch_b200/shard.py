@@ -26,6 +26,26 @@ def my_genes(gene_ids, world: int | None = None, rank: int | None = None):
     return list(gene_ids[lo:hi])
 
 
+def deal(gene_ids, costs, world: int | None = None, rank: int | None = None):
+    """Cost-balanced share of rank: the gene list sorted by expected cost (longest first; ties by id) and dealt
+    round-robin in snake order (0..w-1, w-1..0, ...), so every rank gets the same number of genes (+-1) and nearly
+    the same total cost.  The usual cost is the gene's number of non-zero counts: the tree depth of a sparse gene's
+    posterior is lower.  Deterministic, and the union over ranks is the whole list (tests/test_shard_gloo.py).
+    Results do not depend on the deal: pass the returned ids to api.Batch(gene_ids=...)."""
+    import numpy as np
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    ids = np.asarray(gene_ids)
+    c = np.asarray(costs, dtype=np.float64)
+    if ids.shape[0] != c.shape[0]:
+        raise ValueError("one cost per gene")
+    order = np.lexsort((ids, -c))
+    pos = np.arange(len(order))
+    lap, col = pos // world, pos % world
+    owner = np.where(lap % 2 == 0, col, world - 1 - col)
+    return [int(g) if isinstance(g, (int, np.integer)) else g for g in ids[order[owner == rank]].tolist()]
+
+
 def contiguous_runs(gene_ids, max_len: int):
     """Split a sorted gene-id list into runs of consecutive ids (<= max_len): one device batch each, so
     that `gene_id0 + i` is the gene id that keys the RNG stream."""

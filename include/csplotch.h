@@ -139,6 +139,11 @@ int32_t csplotch_batch_create_dev(csplotch_model *m, const int32_t *counts_dev,
                                   const double *beta_prior_mean, const double *beta_prior_std, int32_t G,
                                   uint32_t gene_id0, void *stream, csplotch_batch **out);
 void csplotch_batch_destroy(csplotch_batch *b);
+/* explicit ids gene_ids[G] of the genes of a batch instead of gene_id0 + g (call before csplotch_sampler_create): the
+ * id keys the RNG stream, so one gene list can be cost-sorted or dealt round-robin over the GPUs (the job array
+ * around /root/reference/bin/splotch:129-133 hands out arbitrary gene indices too) and every gene still gets the
+ * draws it would get alone */
+int32_t csplotch_batch_set_gene_ids(csplotch_batch *b, const uint32_t *gene_ids);
 
 /* ---- model.log_prob_grad<propto=true, jacobian>() of the stanc-generated class ------- */
 /* theta[B][dim], gene_of[B] (index into the batch, or NULL for b % G); lp[B]; grad[B][dim] or NULL */
@@ -161,6 +166,11 @@ int32_t csplotch_write_array(csplotch_batch *b, const double *theta, const int32
 int32_t csplotch_leapfrog_fixed(csplotch_batch *b, const double *theta0, const double *p0,
                                 const double *inv_metric, const int32_t *gene_of, int32_t B, double eps,
                                 int32_t n_steps, double *theta_out, double *p_out, double *H_out);
+
+/* diagnostic (no reference call site): device-timed microbenchmark of the fused leapfrog pass — B trajectories of
+ * n_steps fixed-size steps from deterministic pseudo-random states, average CUDA-event milliseconds of `reps` launches
+ * after one warm-up launch; per launch B * (1 gradient + n_steps leapfrogs) are evaluated, nothing crosses PCIe */
+int32_t csplotch_leapfrog_bench(csplotch_batch *b, int32_t B, double eps, int32_t n_steps, int32_t reps, float *ms_avg);
 
 /* ---- `BINARY sample ...`: hmc_nuts_diag_e_adapt over all genes x chains ----------------
  * (/root/reference/bin/splotch:129-133: one process per chain with num_samples, num_warmup, id;
@@ -185,6 +195,9 @@ int32_t csplotch_sampler_counters(csplotch_sampler *s, int64_t *n_leapfrog, int6
  * candidate copies, everything else}, the number of merge passes and candidate copies, then the cycles of
  * the log-density pass spent before its tile loop (prologue) and after it (reductions, small block) */
 int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out8);
+/* diagnostic: nanoseconds every resident CTA of the last launch was busy (ns[n_slots]; pass ns = NULL to query n_slots):
+ * max - mean is the tail of the launch that the longest-first queue order is there to shorten */
+int32_t csplotch_sampler_slot_ns(csplotch_sampler *s, int64_t *ns, int32_t cap, int32_t *n_slots);
 /* per-chain status [G][num_chains]: 0 ok, 1 initialisation failed, 2 step size search failed */
 int32_t csplotch_sampler_status(csplotch_sampler *s, int32_t *status, int32_t *iters_done);
 

@@ -37,6 +37,14 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_fast() -> str:
+    """The timing build for bench.py's CPU baseline (`make fast`: -O3 -march=native -DORC_FAST).  Always rebuilt on the
+    machine that runs it (-march=native code of another host may not execute here); select it with
+    CSPLOTCH_ORACLE_LIB=<returned path> before the first oracle call.  Never used for parity."""
+    subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "fast"])
+    return os.path.join(_HERE, "_build", "libcsplotch_oracle_fast.so")
+
+
 class _OrcData(C.Structure):
     _fields_ = [
         ("family", C.c_int32),

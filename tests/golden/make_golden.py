@@ -12,6 +12,7 @@ that runs is the reference's own code:
              coordinates + AARs; count tables are missing upstream, so sequencing depth is stubbed)
   io/        to_rdump / read_rdump / read_stan_csv round-trip vectors for the I/O tests
   snap25_head.npz   first tissues of Science/human/data_SNAP25.R parsed with the reference's read_rdump
+  snap25_full.npz   the whole file (`python tests/golden/make_golden.py snap25_full`)
 """
 import importlib.machinery
 import importlib.util
@@ -196,7 +197,29 @@ def make_snap25(U):
     print("snap25 head: N=%d pairs=%d (full N=%d)" % (n, len(W), int(np.sum(d["N_spots"]))))
 
 
+def make_snap25_full():
+    """The WHOLE Science/human/data_SNAP25.R (80 tissue sections, N = 61 031, W_n = 112 012, the file's own eig_values with
+    88 entries exactly +1): the shape the full-size parity tests use.  Parsed with the
+    whitespace-tolerant product reader for the reason stated in make_snap25()."""
+    path = os.path.join(REF, "Science", "human", "data_SNAP25.R")
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from csplotch_b200.rdump import read_rdump
+    d = read_rdump(path)
+    np.savez_compressed(os.path.join(OUT, "snap25_full.npz"),
+                        N_spots=np.asarray(d["N_spots"], dtype=np.int32), tissue_mapping=np.asarray(d["tissue_mapping"], dtype=np.int32),
+                        donor_mapping=np.asarray(d["donor_mapping"], dtype=np.int32), N_donors=int(d["N_donors"]),
+                        N_onsets_tissue_locations=int(d["N_onsets_tissue_locations"]), N_covariates=int(d["N_covariates"]),
+                        size_factors=np.asarray(d["size_factors"]), counts=np.asarray(d["counts"], dtype=np.int32),
+                        D=np.asarray(d["D"], dtype=np.int8), D_sparse=np.asarray(d["D_sparse"], dtype=np.int8),
+                        W_sparse=np.asarray(d["W_sparse"], dtype=np.int32), eig_values=np.asarray(d["eig_values"]))
+    print("snap25 full: N=%d pairs=%d eig==1: %d" % (int(np.sum(d["N_spots"])), len(d["W_sparse"]),
+                                                     int(np.sum(np.asarray(d["eig_values"]) == 1.0))))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "snap25_full":
+        make_snap25_full()
+        sys.exit(0)
     U, gen = load_reference()
     make_io(U)
     make_c1(U, gen)

@@ -107,7 +107,7 @@ def test_gpu_arm_control_flow_with_mocked_device(tmp_path):
         assert key in d, key
     assert d["metric"] == "grad_evals_per_sec" and d["dtype"] == "f64" and d["vs_baseline"] is None
     assert "workload" in d["config"] and "model" not in d["config"]
-    assert d["steps"] == 2 and d["gpu_launches"] == 2 and d["n_gpus"] == 1 and d["scaling"] == "weak"
+    assert d["steps"] == 2 and d["gpu_launches"] == 2 and d["n_gpus"] == 1 and d["scaling"] == "strong"
     # 2 steps x 1 transition x 100 "gradients" in 2 x 5 ms of "device time" (the mock's counters)
     assert abs(d["value"] - 2 * 100 * d["config"]["nuts_transitions_per_chain_per_step"] / 0.010) < 1e-6
     rf = d["roofline"]
@@ -117,4 +117,7 @@ def test_gpu_arm_control_flow_with_mocked_device(tmp_path):
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["unit"] == d["unit"]
     assert d["ess"]["genes"] == 2 and d["ess"]["num_samples"] == 10 and "beta_only" in d["ess"]
+    assert d["genes_per_hour_to_ess400"] == d["ess"]["genes_per_hour_to_ess400"] and d["ess"]["transcriptome_20k_genes_minutes"] > 0
+    assert abs(rf["launch_tail_frac"] - 0.1) < 1e-9 and abs(sum(rf["time_shares"].values()) - 1) < 1e-9
+    assert "EXTRAPOLATED" in (rf["traffic_source"] or "EXTRAPOLATED")
     assert "ESS leg done" in r.stderr and "e2e arm" in r.stderr

@@ -27,10 +27,10 @@ def _fake_sample(gene_id, seed=7):
     return {"ess": float(rng.uniform(100, 900)), "n_leapfrog": int(rng.integers(1000, 5000))}
 
 
-def _worker(rank, world, port, genes, q):
+def _worker(rank, world, port, genes, q, costs=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    mine = shard.my_genes(genes)
+    mine = shard.my_genes(genes) if costs is None else shard.deal(genes, costs)   # bench.py's strong-scaling deal
     local = {g: _fake_sample(g) for g in mine}
     t = torch.tensor([float(len(mine))])
     dist.all_reduce(t)                      # the barrier + reduction pattern bench.py uses
@@ -57,6 +57,44 @@ def test_two_rank_gloo_sharding():
     assert sorted(allres) == genes
     for g in genes:
         assert allres[g] == _fake_sample(g)  # identical whichever rank sampled it
+
+
+def test_two_rank_gloo_cost_sorted_deal():
+    """the strong-scaling path of bench.py (c5): one gene list dealt longest-first over the ranks, results keyed by gene id"""
+    genes = list(range(3, 26))
+    costs = [int(x) for x in np.random.default_rng(1).integers(0, 5000, len(genes))]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, genes, q, costs)) for r in range(2)]
+    for p in procs:
+        p.start()
+    allres, total = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert total == len(genes) and sorted(allres) == genes
+    for g in genes:
+        assert allres[g] == _fake_sample(g)
+
+
+def test_deal_properties():
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 23, 592, 2368):
+        ids = np.arange(100, 100 + n)
+        cost = rng.integers(0, 120000, n)
+        for w in (1, 2, 4, 8):
+            parts = [shard.deal(ids, cost, w, r) for r in range(w)]
+            assert sorted(sum(parts, [])) == ids.tolist()                       # a partition of the list
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 1
+            if n >= 8 * w:
+                tot = [sum(int(cost[g - 100]) for g in p) for p in parts]
+                assert max(tot) - min(tot) <= 2 * cost.max()                   # snake deal: totals within two items
+            for p in parts:                                                    # longest first inside a share
+                c = [int(cost[g - 100]) for g in p]
+                assert c == sorted(c, reverse=True)
+            assert parts == [shard.deal(ids, cost, w, r) for r in range(w)]    # deterministic
 
 
 def test_block_partition_properties():

@@ -36,8 +36,9 @@ class _Model:
 
 
 class _Batch:
-    def __init__(self, model, counts, beta_prior_mean=None, beta_prior_std=None, gene_id0=0):
+    def __init__(self, model, counts, beta_prior_mean=None, beta_prior_std=None, gene_id0=0, gene_ids=None):
         self.model, self.gene_id0 = model, gene_id0
+        self.gene_ids = gene_ids
         counts = np.asarray(counts).reshape(-1, model.N)
         self.G = len(counts)
         self.beta_prior_mean = None if beta_prior_mean is None else np.asarray(beta_prior_mean, dtype=float).reshape(self.G, -1)
@@ -81,7 +82,8 @@ class _Sampler:
         for g in range(self.G):
             for c in range(self.nch):
                 qi = None if self.theta_init is None else self.theta_init[g, c]
-                out = self.batch.o[g].nuts(ocfg, gene_id=self.batch.gene_id0 + g, chain_id=c + 1, q_init=qi)
+                out = self.batch.o[g].nuts(ocfg, gene_id=(self.batch.gene_id0 + g) if self.batch.gene_ids is None else int(self.batch.gene_ids[g]),
+                                              chain_id=c + 1, q_init=qi)
                 self._status[g, c] = out["status"]
                 self._diag[g, c], self._theta[g, c] = out["draws"][:, :7], out["draws"][:, 7:]
         return self

@@ -24,6 +24,8 @@ class Sampler(fakes._Sampler):
     def advance(self, n, sync=True):
         self._adv += n; self._calls += 1
     def last_ms(self): return 5.0
+    def launch_tail(self): return 0.9, 1.0
+    def profile(self): return dict(cyc_eval=80, cyc_merge=15, cyc_copy=1, cyc_other=4, n_merge=1, n_copy=1, cyc_pro=1, cyc_fin=1)
     def run(self, chunk=None):
         super().run(chunk); self._ran = True; self.total_ms = 12.0; self._calls += 1; return self
     def counters(self):
@@ -40,13 +42,16 @@ class Sampler(fakes._Sampler):
         return {k: np.ones((self.G, N)) for k in ("log_lambda/mean", "log_lambda/std", "lambda/mean", "lambda/std", "psi/mean", "psi/std")}
     def close(self): pass
 
-api.Model, api.Batch, api.Sampler = fakes._Model, Batch, Sampler
+class Model(fakes._Model):
+    def close(self): pass
+
+api.Model, api.Batch, api.Sampler = Model, Batch, Sampler
 gdir = os.path.join(ROOT, "tests", "golden", "c1")
 datas = [rdump.read_rdump(os.path.join(gdir, "data_%d.R" % g)) for g in (1, 2, 3)]
 shared = {k: v for k, v in datas[0].items() if k not in rdump.GENE_KEYS}
 genes = {k: np.stack([d[k] for d in datas]) for k in rdump.GENE_KEYS}
 bench.make_inputs = lambda workload, G, rank, head_only=False: ("comp_splotch_stan_model", shared, genes)
 sys.argv = ["bench.py", "--steps", "2", "--warmup", "1", "--no-cpu", "--genes", "3", "--e2e-genes", "2", "--e2e-iters", "8",
-            "--ess-genes", "2", "--ess-n", "10"]
+            "--ess-genes", "2", "--ess-n", "10", "--no-secondary"]
 rc = bench.main()
 print("rc", rc, file=sys.stderr)
