@@ -20,7 +20,7 @@ CUDA events on the sampler's stream, max over ranks.
   roofline   dominant kernel k_nuts_advance: algorithmic bytes (B_leap = 56 D + 4 N per
              in-sampler leapfrog, B_grad = 16 D + 4 N per other gradient) / CUDA-event duration vs the
              measured HBM peak (MEASURED_PEAKS.json); fp64_frac = fp64 flops per gradient / measured DFMA peak
-  ess        a complete `splotch -n 200 -c 4` job of 74 genes per GPU: genes / hour, genes / hour to bulk-ESS >= 400
+  ess        a complete `splotch -n 200 -c 4` job of 16 genes per GPU: genes / hour, genes / hour to bulk-ESS >= 400
              (all parameters, and betas only), minutes for a 20 000-gene transcriptome at that rate
   secondary  (N = 1) the c2 shape (BASELINE configs[1]) resident-arm rate and roofline fraction
   cpu_baseline  the CPU oracle (restatement of the Stan models + Stan's NUTS; CmdStan itself is not
@@ -295,7 +295,7 @@ def main():
     ap.add_argument("--e2e-iters", type=int, default=0, help="NUTS transitions per chain in one e2e step")
     ap.add_argument("--ess-genes", type=int, default=-1,
                     help="genes per GPU of the `splotch -n N -c 4` job behind genes/hour to bulk-ESS >= 400 "
-                         "(default 74 = one resident wave of gene-chains at c3; 0 skips the leg)")
+                         "(default 16 at c3: 64 gene-chains, one resident wave of 4-CTA clusters; 0 skips the leg)")
     ap.add_argument("--ess-n", type=int, default=200, help="N of that job (the reference's README uses -n 200)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the c2 sub-record (N = 1)")
     args = ap.parse_args()
@@ -393,8 +393,8 @@ def main():
     # path: counts of Ge genes (page-locked host memory) -> Batch (H2D) -> Sampler -> warm-up + sampling
     # transitions from initialisation -> draws of the non-spot block + posterior summaries of every spot (D2H
     # into page-locked host arrays).  The page-locked buffers are allocated once, outside the timed region.
-    Ge = min(G, args.e2e_genes or (4736 if N < 10000 else 148))
-    e2e_iters = args.e2e_iters or (50 if N < 10000 else 10)
+    Ge = min(G, args.e2e_genes or (4736 if N < 10000 else 74))
+    e2e_iters = args.e2e_iters or (50 if N < 10000 else 20)
     e_warm, e_samp = e2e_iters // 2, e2e_iters - e2e_iters // 2
     counts_host = api.pinned_empty((Ge, N), np.int32)
     counts_host[...] = genes["counts"][:Ge]
@@ -432,7 +432,7 @@ def main():
 
     # ---- genes / hour to bulk-ESS >= 400 (second half of the BASELINE metric) ------------------------------
     ess = None
-    ess_genes = args.ess_genes if args.ess_genes >= 0 else (74 if N >= 10000 else 592)
+    ess_genes = args.ess_genes if args.ess_genes >= 0 else (16 if N >= 10000 else 592)
     if ess_genes > 0:
         ess = ess_leg(api, model, genes, min(G, ess_genes), args.ess_n, args.chains, gene_ids=gene_ids)
         note("ESS leg done (%d genes, -n %d, %.1f s)" % (ess["genes"], args.ess_n, ess["device_seconds"]))

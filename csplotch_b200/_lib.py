@@ -51,9 +51,9 @@ SYMBOLS = [
     "csplotch_log_prob_grad", "csplotch_log_prob_grad_dev", "csplotch_write_array", "csplotch_leapfrog_fixed", "csplotch_leapfrog_bench",
     "csplotch_nuts_cfg_default", "csplotch_sampler_create", "csplotch_sampler_destroy", "csplotch_sampler_init",
     "csplotch_sampler_advance", "csplotch_sampler_sync", "csplotch_sampler_last_ms", "csplotch_sampler_counters",
-    "csplotch_sampler_status", "csplotch_sampler_slot_ns", "csplotch_sampler_profile", "csplotch_sampler_get_draws", "csplotch_sampler_get_theta_draws",
+    "csplotch_sampler_status", "csplotch_sampler_slot_ns", "csplotch_sampler_layout", "csplotch_sampler_profile", "csplotch_sampler_get_draws", "csplotch_sampler_get_theta_draws", "csplotch_sampler_get_theta_draws_range",
     "csplotch_sampler_get_state", "csplotch_sampler_get_spot_summaries", "csplotch_rdump_read_genes", "csplotch_host_alloc", "csplotch_host_free",
-    "csplotch_csv_write",
+    "csplotch_csv_write", "csplotch_car_precompute",
 ]
 
 _lib = None

@@ -118,6 +118,12 @@ class Model:
                     raise CsplotchError("U must have N+1 entries")
                 if not W_n:
                     W_n = k["V"].size // 2
+            if not np.size(d.get("eig_values", [])) or not np.size(d.get("D_sparse", [])):
+                # a dictionary without the CAR pre-compute (generate_dictionary's eigvalsh block, utils.py:749-759):
+                # done here on the GPU; tissues beyond 9 999 spots need `coords` for the chunked solution
+                from . import car as _car
+                pre = _car.precompute(k["N_spots"], np.asarray(d["W_sparse"]).reshape(W_n, 2), coords=d.get("coords"))
+                d = dict(d, eig_values=pre["eig_values"], D_sparse=pre["D_sparse"])
             k["Ds"] = _f64(d["D_sparse"])
             k["eig"] = _f64(d["eig_values"])
             if k["Ds"].size != N or k["eig"].size != N:
@@ -421,6 +427,12 @@ class Sampler:
         keys = ["cyc_eval", "cyc_merge", "cyc_copy", "cyc_other", "n_merge", "n_copy", "cyc_pro", "cyc_fin"]
         return dict(zip(keys, [int(x) for x in out]))
 
+    def layout(self):
+        """(gene-chains resident at once, CTAs of the thread-block cluster working on each)"""
+        a, b = C.c_int32(), C.c_int32()
+        check(self.lib.csplotch_sampler_layout(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def launch_tail(self):
         """Diagnostic: (mean, max) busy seconds over the resident CTAs of the last launch; 1 - mean / max is the
         fraction of the launch the average SM slot spent idle waiting for the longest chain."""
@@ -452,9 +464,12 @@ class Sampler:
         check(self.lib.csplotch_sampler_get_draws(self.h, _p(diag), _p(small), _p(nd)))
         return diag, small, nd
 
-    def theta_draws(self):
-        out = np.empty((self.G, self.nch, self.cfg.num_samples, self.model.dim))
-        check(self.lib.csplotch_sampler_get_theta_draws(self.h, _p(out)))
+    def theta_draws(self, g0: int = 0, n_genes: int | None = None):
+        """every sampling draw of the unconstrained vector, (n_genes, chains, S, dim), for genes g0 .. g0 + n_genes - 1 of
+        the batch (default: all — at 10^5 spots fetch a few genes at a time)"""
+        n = self.G - g0 if n_genes is None else int(n_genes)
+        out = np.empty((n, self.nch, self.cfg.num_samples, self.model.dim))
+        check(self.lib.csplotch_sampler_get_theta_draws_range(self.h, C.c_int32(g0), C.c_int32(n), _p(out)))
         return out
 
     def state(self):

@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "csplotch.cu")
 HOST_SRC = os.path.join(HERE, "csrc", "ingest.cpp")   # host-only part of the ABI (R-dump fast path)
-DEPS = [SRC, HOST_SRC] + [os.path.join(HERE, "csrc", f) for f in ("device_ops.cuh", "nuts_core.h", "philox.h", "fastmath.h")] + [
+CAR_SRC = os.path.join(HERE, "csrc", "car_precompute.cu")   # CAR pre-compute (cuSOLVER through dlopen)
+DEPS = [SRC, HOST_SRC, CAR_SRC] + [os.path.join(HERE, "csrc", f) for f in ("device_ops.cuh", "nuts_core.h", "philox.h", "fastmath.h")] + [
     os.path.join(ROOT, "include", "csplotch.h")]
 OUT = os.path.join(HERE, "libcsplotch_b200.so")
 
@@ -17,6 +18,7 @@ NVCC_FLAGS = [
     "-ccbin", "/usr/bin/g++",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    "--split-compile", "0",     # the kernels of this one translation unit are optimised on all host cores
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
@@ -45,7 +47,7 @@ def build(force: bool = False, verbose: bool = False, dev: bool = False, out: st
         return OUT
     out = (out or DEV_OUT) if dev else OUT
     cmd = ([nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DCSPLOTCH_DEV_KT"] + os.environ.get("CSPLOTCH_DEV_DEFS", "").split() if dev else [])
-           + ["-o", out, SRC, HOST_SRC])
+           + ["-o", out, SRC, HOST_SRC, CAR_SRC, "-ldl"])
     subprocess.check_call(cmd)
     return out
 

@@ -4,8 +4,9 @@
 
 `-b BINARY`: the basename (splotch_stan_model | comp_splotch_stan_model | splotch_stan_model_csr) selects
 the model family; no CmdStan executable is run.  Additive: `-g` also accepts ranges / lists
-("1-2000", "3,7,9-12") so one process samples thousands of genes at once on the GPU, `--gpus N` shards the
-gene list over N devices (one process each, no collective), `--seed`.
+("1-2000", "3,7,9-12") so one process samples thousands of genes at once on the GPU, and `--seed`.  Several GPUs:
+launch one process per device with torchrun (`python -m torch.distributed.run --nproc-per-node N -m csplotch_b200.cli
+...`); every rank takes its block of the gene list (WORLD_SIZE / RANK / LOCAL_RANK), no collective.
 
 Inputs are the unchanged `DATA/<g//100>/data_<g>.R` files of splotch_generate_input_files; outputs are
 `OUT/<g//100>/combined_<g>.csv` (header + draws, chain-major, no comments) or, with -s,
@@ -93,7 +94,6 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
     status, iters = s.status()
     cols = model.column_names()
     written = []
-    theta = s.theta_draws() if not summary else None
     diag, _, _ = s.draws()
     good = []
     for i, g in enumerate(gene_ids):
@@ -117,7 +117,8 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
         step = max(1, min(os.cpu_count() or 1, (1 << 30) // max(1, 8 * rows * model.n_outputs)))
         for a0 in range(0, len(good), step):
             blk = good[a0:a0 + step]
-            th = theta[blk].reshape(-1, model.dim)
+            # the draws of this block only (the whole batch at once can exceed host memory at c3-scale dimensions)
+            th = np.concatenate([s.theta_draws(g0=i, n_genes=1) for i in blk]).reshape(-1, model.dim)
             vals = batch.write_array(th, gene_of=np.repeat(np.asarray(blk, dtype=np.int32), rows))
             paths = [os.path.join(out_dir, str(gene_ids[i] // 100), "combined_%d.csv" % gene_ids[i]) for i in blk]
             stancsv.write_combined_csvs(paths, cols, diag[blk].reshape(len(blk), rows, 7),
@@ -130,6 +131,8 @@ def sample_genes(shared, genes, family, gene_ids, out_dir, num_samples, num_chai
             if pf_rep is not None:
                 rep["pathfinder"] = pf_rep
             f.write(json.dumps(rep) + "\n")
+    # genes that wrote no combined_<g>.* file: the caller exits non-zero like the reference's error_exit (bin/splotch:131)
+    s.failed_genes = [int(g) for i, g in enumerate(gene_ids) if i not in set(good)]
     return written, s
 
 
@@ -244,12 +247,14 @@ def main(argv=None, vinit=False):
         try:
             shared, genes = load_genes(a.d, run)
             if vinit:
-                sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device,
-                             num_warmup=VINIT_NUM_WARMUP, vinit=dict(max_lbfgs_iters=a.max_lbfgs_iters),
-                             sig_figs=a.sig_figs, report=a.report)
+                _, smp = sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device,
+                                      num_warmup=VINIT_NUM_WARMUP, vinit=dict(max_lbfgs_iters=a.max_lbfgs_iters),
+                                      sig_figs=a.sig_figs, report=a.report)
             else:
-                sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device,
-                             sig_figs=a.sig_figs, report=a.report)
+                _, smp = sample_genes(shared, genes, a.b, run, a.o, a.n, a.c, a.s, seed=seed, device=a.device,
+                                      sig_figs=a.sig_figs, report=a.report)
+            if getattr(smp, "failed_genes", None):
+                rc = 1     # a gene without output is a failed run for job arrays and schedulers
         except Exception as e:  # noqa: BLE001
             print("Error: Stan run failed! (%s)" % e, file=sys.stderr)
             rc = 1

@@ -75,7 +75,32 @@ struct csplotch_model {
   int kt = 1;             // template instantiation (max K)
   size_t smem_bytes = 0;
   int n_outputs = 0;
+  // thread-block cluster variants of the design (DevModel::cl): tile partition + the ELL table with halo positions
+  struct ClusterVariant { int cl; int t0[kMaxCluster + 1]; unsigned short *ell_dev; };
+  std::vector<ClusterVariant> clv;
+  int max_cl = 1;        // the largest cluster size worth using on this design (by its tile count)
+  int forced_cl = 0;     // CSPLOTCH_CLUSTER at model creation (tests / A-B measurements): always use this size
 };
+
+// the model descriptor of a launch with clusters of `cl` CTAs (cl == 1: the plain one)
+static DevModel with_cluster(const csplotch_model *m, int cl) {
+  DevModel d = m->dm;
+  d.cl = 1;
+  d.ell_cl = d.ell;
+  for (int r = 0; r <= kMaxCluster; ++r) d.cl_t0[r] = r == 0 ? 0 : d.NT;
+  for (const auto &v : m->clv)
+    if (v.cl == cl) {
+      d.cl = cl;
+      d.ell_cl = v.ell_dev;
+      for (int r = 0; r <= kMaxCluster; ++r) d.cl_t0[r] = v.t0[r];
+    }
+  return d;
+}
+static bool has_cluster(const csplotch_model *m, int cl) {
+  for (const auto &v : m->clv)
+    if (v.cl == cl) return true;
+  return cl == 1;
+}
 
 struct csplotch_batch {
   csplotch_model *m = nullptr;
@@ -116,6 +141,8 @@ struct csplotch_sampler {
   bool timed = false;
   int grid = 0;
   int64_t launches = 0;
+  int cl = 1;                        // CTAs per gene-chain of this sampler's launches (choose_cluster)
+  DevModel dml;                      // the model descriptor with that cluster partition
   int *order_dev = nullptr;          // [W] queue order of the next launch
   std::vector<double> nnz_host;      // [G] non-zero counts per gene: the cost estimate before the first transition
   std::vector<ChainScalars> cs_host;
@@ -217,19 +244,28 @@ __device__ __forceinline__ void stage_model(DevModel &dst, const DevModel &src) 
 }
 
 // dynamic shared memory: B[nbeta] | adjB[nbeta] | red | mbar[10] | tdesc | ring[4T or 8T] + zero cell | psi slots | rest slots
-template <int KT>
-__device__ __forceinline__ void bind_smem(DevOps<KT> &ops, const DevModel &m, double *smem) {
-  ops.B = smem;
-  ops.adjB = smem + m.nbeta;
-  ops.red = smem + 2 * m.nbeta;
-  double *p = ops.red + kWarps * kRedMax;
+constexpr int kClScratch = 16 + 4 + 16 + 12 + 8;  // doubles: cl_part | cl_bcast | cl_red[2][8] | cl_sc | sraw
+template <class Ops>
+__device__ __forceinline__ void bind_smem(Ops &ops, const DevModel &m, double *smem) {
+  ops.B_o = 0;
+  ops.adjB_o = m.nbeta;
+  ops.red_o = 2 * m.nbeta;
+  double *p = smem + 2 * m.nbeta + kWarps * kRedMax;
   ops.mbar = reinterpret_cast<uint64_t *>(p);
   p += 10;
+  ops.cl_part = p;
+  ops.cl_bcast = p + 16;
+  ops.cl_red = p + 20;
+  ops.cl_sc = p + 36;
+  ops.sraw_o = (int)(p + 48 - smem);
+  p += kClScratch;
   ops.tdesc = reinterpret_cast<TmaDesc *>(p);
   p += (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 2;
   const int ring_tiles = m.look == 1 ? 4 : 8;
   ops.ring = p;
   p += ring_tiles * kTile + 2;  // + the always-zero cell missing neighbours point at
+  ops.halo = p;                 // cluster kernels: psi of the tiles next to this rank's range (ell_cl positions)
+  if (m.cl > 1) p += 2 * m.look * kTile;
   ops.psi_st = p;
   p += (m.look + 2) * 4 * kTile;
   ops.rest_st = reinterpret_cast<unsigned char *>(p);
@@ -283,7 +319,7 @@ __global__ void k_negate(double *v, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] = -v[i];
 }
 
-template <int KT>
+template <int KT, bool CL>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
 k_leapfrog_fixed(const __grid_constant__ DevModel m_in, const int *__restrict__ counts, const double *__restrict__ pm,
                  const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz,
@@ -294,10 +330,12 @@ k_leapfrog_fixed(const __grid_constant__ DevModel m_in, const int *__restrict__ 
   __shared__ DevModel s_model;
   stage_model(s_model, m_in);
   const DevModel &m = s_model;
-  DevOps<KT> ops(m);
+  DevOps<KT, CL> ops(m);
   bind_smem(ops, m, smem_d);
+  ops.bind_cluster();
   ops.jacobian = 1;
-  for (int b = blockIdx.x; b < Bn; b += gridDim.x) {
+  // one trajectory per CTA, or per cluster of m.cl CTAs
+  for (int b = blockIdx.x / ops.csize; b < Bn; b += gridDim.x / ops.csize) {
     const int gi = gene_of ? gene_of[b] : (b % G);
     ops.gn.counts = counts + (size_t)gi * m.Nc;
     ops.gn.pm = pm ? pm + (size_t)gi * m.K : nullptr;
@@ -312,40 +350,51 @@ k_leapfrog_fixed(const __grid_constant__ DevModel m_in, const int *__restrict__ 
     for (int s = 0; s < n_steps; ++s) ops.template eval<true>(qb, gb, pb, qb, gb, pb, eps, &V, &K, nullptr);
     if (n_steps == 0) {
       double k = 0.0;
-      for (int e = threadIdx.x; e < m.Di; e += kBlock) k += ops.minv[e] * pb[e] * pb[e];
+      for (int sgi = 0; sgi < ops.nseg; ++sgi)
+        for (int e = ops.seg_lo[sgi] + threadIdx.x; e < ops.seg_hi[sgi]; e += kBlock) k += ops.minv[e] * pb[e] * pb[e];
       double r[1] = {k};
-      block_sum<1>(r, ops.red);
+      ops.template chain_sum<1>(r);
       K = 0.5 * r[0];
     }
-    if (threadIdx.x == 0) H_out[b] = V + K;
+    if (threadIdx.x == 0 && ops.crank == 0) H_out[b] = V + K;
     __syncthreads();
   }
+  ops.cluster_sync();   // no CTA of a cluster leaves while another may still read its shared memory
 }
 
-template <int KT>
+template <int KT, bool CL>
 __global__ void __launch_bounds__(kBlock, kCtasPerSm<KT>)
 k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ SamplerDev s, int n_iter) {
   __shared__ int s_work;
   const size_t Di = m_in.Di;
   long long t_start_ns = 0;
   if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
-  double *ws = s.ws + (size_t)blockIdx.x * (size_t)(s.pool_vecs + 6) * Di;
   // the model descriptor is read all over the per-evaluation prologue / epilogue: a shared-memory copy turns
   // those dependent generic loads from the parameter bank into LDS
   __shared__ DevModel s_model;
   stage_model(s_model, m_in);
   const DevModel &m = s_model;
-  DevOps<KT> ops(m);
+  DevOps<KT, CL> ops(m);
   bind_smem(ops, m, smem_d);
+  ops.bind_cluster();
+  // workspace slot of this CTA, or of its cluster (every rank touches only its own element ranges)
+  double *ws = s.ws + (size_t)(blockIdx.x / ops.csize) * (size_t)(s.pool_vecs + 6) * Di;
   ops.jacobian = 1;
   for (;;) {
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && ops.crank == 0) {
       const int t = atomicAdd(s.queue, 1);
       s_work = t < s.W ? s.order[t] : -1;
     }
-    __syncthreads();
-    const int w = s_work;
-    __syncthreads();
+    int w;
+    if (CL && ops.csize > 1) {
+      ops.cluster_sync();
+      w = *ops.remote(&s_work, 0);
+      ops.cluster_sync();   // rank 0 may pop again only after every rank has read this one
+    } else {
+      __syncthreads();
+      w = s_work;
+      __syncthreads();
+    }
     if (w < 0) break;
     const int g = w / s.num_chains, c = w - g * s.num_chains;
     ops.gn.counts = s.counts + (size_t)g * m.Nc;
@@ -374,10 +423,11 @@ k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ Sa
     ChainScalars cs = s.cs[w];
     ops.cyc_eval = ops.cyc_merge = ops.cyc_copy = ops.cyc_other = ops.n_merge = ops.n_copy = ops.cyc_pro = ops.cyc_fin = 0;
     const long long t_chain = clock64();
-    Nuts<DevOps<KT>> nuts(ops, s.cfg, cs, ops.key);
+    Nuts<DevOps<KT, CL>> nuts(ops, s.cfg, cs, ops.key);
     nuts.advance(n_iter, s.have_init != 0);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    // (cluster: every rank has read this chain's scalars before rank 0 overwrites them)
+    if (CL && ops.csize > 1) ops.cluster_sync(); else __syncthreads();
+    if (threadIdx.x == 0 && ops.crank == 0) {
       cs.cyc_eval += ops.cyc_eval; cs.cyc_merge += ops.cyc_merge; cs.cyc_copy += ops.cyc_copy;
       cs.n_merge += ops.n_merge; cs.n_copy += ops.n_copy; cs.cyc_pro += ops.cyc_pro; cs.cyc_fin += ops.cyc_fin;
       cs.cyc_other += (clock64() - t_chain) - ops.cyc_eval - ops.cyc_merge - ops.cyc_copy;
@@ -624,11 +674,37 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     for (int i = 0; i < N; ++i) ell_w = std::max(ell_w, (int)adj0[i].size());
   dm.tiled = tiled ? 1 : 0;
   dm.look = tiled ? std::max(1, reach(m->perm)) : 1;
-  if (dm.look == 2 && kt > 2) { tiled = false; dm.tiled = 0; dm.look = 1; }  // reach 2 is built for the non-compositional kernels only
   dm.ell_w = (car && tiled) ? ell_w : 0;
   dm.stage_bytes = (5 * kTile) * (int)sizeof(double) + 2 * kTile * (int)sizeof(int) + ((dm.ell_w + 1) / 2 * 2) * kTile * (int)sizeof(unsigned short);
-  m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 10) * sizeof(double) + (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 16;
+  // gene-chains of long designs can run on a thread-block cluster (DevModel::cl); the partitions are prepared here,
+  // the size is chosen per launch from the number of gene-chains (choose_cluster)
+  dm.cl = 1;
+  for (int r = 0; r <= kMaxCluster; ++r) dm.cl_t0[r] = r == 0 ? 0 : dm.NT;
+  if (tiled) {
+    m->max_cl = dm.NT >= 160 ? 4 : (dm.NT >= 64 ? 2 : 1);
+    if (const char *fc = std::getenv("CSPLOTCH_CLUSTER")) {
+      const int f = std::atoi(fc);
+      if (f == 1 || f == 2 || f == 4 || f == 8) m->forced_cl = f;
+    }
+    const int min_tiles = dm.look + 3;
+    for (int cl = 2; cl <= kMaxCluster; cl *= 2) {
+      if (dm.NT < cl * min_tiles) break;
+      if (cl > m->max_cl && cl != m->forced_cl) continue;
+      csplotch_model::ClusterVariant v;
+      v.cl = cl;
+      v.ell_dev = nullptr;
+      // equal shares: rank 0's epilogue of the small block runs after every rank's tiles are done (it needs their
+      // partial sums), so giving rank 0 fewer tiles would only lengthen the others' share (measured: 107 / 120 tiles
+      // at c3 cost 2 % against 117 / 117)
+      for (int r = 0; r <= cl; ++r) v.t0[r] = (int)((long long)dm.NT * r / cl);
+      for (int r = cl + 1; r <= kMaxCluster; ++r) v.t0[r] = dm.NT;
+      m->clv.push_back(v);
+    }
+    if (m->forced_cl > 1 && !has_cluster(m, m->forced_cl)) m->forced_cl = m->clv.empty() ? 1 : m->clv.back().cl;
+  }
+  m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 10 + kClScratch) * sizeof(double) + (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 16;
   if (tiled) m->smem_bytes += ((size_t)((dm.look == 1 ? 4 : 8) + 4 * (dm.look + 2)) * kTile + 2) * sizeof(double) + 2 * (size_t)dm.stage_bytes;
+  if (!m->clv.empty()) m->smem_bytes += (size_t)2 * dm.look * kTile * sizeof(double);
   if (m->smem_bytes > 220 * 1024) {
     delete m;
     return fail(CSPLOTCH_E_UNSUPPORTED, "beta table (L*C*K) too large for shared memory");
@@ -684,6 +760,28 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
         for (size_t w = 0; w < a.size(); ++w)
           ell[((size_t)(i / kTile) * dm.ell_w + w) * kTile + (i % kTile)] = (unsigned short)(a[w] & (ring_n - 1));
     }
+    // the clusters' tables: a neighbour outside the tile range of the spot's rank lives in that rank's halo cells
+    for (auto &v : m->clv) {
+      std::vector<unsigned short> ec = ell;
+      std::vector<int> rank_of_tile(dm.NT, 0);
+      for (int r = 0; r < v.cl; ++r)
+        for (int t = v.t0[r]; t < v.t0[r + 1]; ++t) rank_of_tile[t] = r;
+      for (int i = 0; i < N; ++i) {
+        const int r = rank_of_tile[i / kTile], ta = v.t0[r], tb = v.t0[r + 1];
+        for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+          const int a = col[e], t = a / kTile;
+          int pos;
+          if (t >= ta && t < tb) continue;
+          if (t < ta) pos = ring_n + 2 + (a - (ta - dm.look) * kTile);
+          else pos = ring_n + 2 + dm.look * kTile + (a - tb * kTile);
+          ec[((size_t)(i / kTile) * dm.ell_w + (e - rowptr[i])) * kTile + (i % kTile)] = (unsigned short)pos;
+        }
+      }
+      if (m->buf.upload(&v.ell_dev, ec) != cudaSuccess) {
+        delete m;
+        return fail(CSPLOTCH_E_CUDA, "model upload failed (cluster table)");
+      }
+    }
     // distinct eigenvalues with multiplicity (exact duplicates only; c3 has 24 identical arrays)
     std::map<double, double> mult;
     for (int i = 0; i < N; ++i) mult[d->eig_values[i]] += 1.0;
@@ -731,7 +829,7 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     delete m;
     return fail(CSPLOTCH_E_CUDA, "model upload failed: " + msg);
   }
-  dm.lsf = p_lsf; dm.key = p_key; dm.rowptr = p_rp; dm.col = p_col; dm.ell = p_ell; dm.E = p_E; dm.eigu = p_eu; dm.eigm = p_em; dm.eigg = p_eg; dm.eiggm = p_egm;
+  dm.lsf = p_lsf; dm.key = p_key; dm.rowptr = p_rp; dm.col = p_col; dm.ell = p_ell; dm.ell_cl = p_ell; dm.E = p_E; dm.eigu = p_eu; dm.eigm = p_em; dm.eigg = p_eg; dm.eiggm = p_egm;
   dm.map2 = p_m2; dm.map3 = p_m3; dm.imap = p_imap;
   *out = m;
   return CSPLOTCH_OK;
@@ -859,6 +957,65 @@ static cudaError_t set_smem(Kern kern, size_t bytes) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// Cluster size for `n_chains` gene-chains: the smallest size that leaves >= 8 work units per resident slot (the tail
+// of a launch is about 0.8 / units of its length: measured 10 % at 8), at most what the design supports.  Few chains
+// (one gene block of bin/splotch, the ESS job, a strong-scaling share) thus run on 4-CTA clusters, thousands of
+// chains on plain CTAs, whose throughput is 5-10 % higher (no serial rank-0 epilogue).
+static int choose_cluster(const csplotch_model *m, long long n_chains) {
+  if (m->forced_cl) return m->forced_cl;
+  const long long slots = (long long)sm_count() * ctas_per_sm(m->kt);
+  int cl = 1;
+  while (cl < m->max_cl && has_cluster(m, 2 * cl) && n_chains * cl < 8 * slots) cl *= 2;
+  return cl;
+}
+
+// kernels that run one gene-chain per CTA (CLV = false) or per thread-block cluster of CTAs (CLV = true)
+#define DISPATCH_KT_CL(kt, clustered, ...)                                      \
+  if (clustered) { constexpr bool CLV = true; DISPATCH_KT(kt, __VA_ARGS__) }    \
+  else { constexpr bool CLV = false; DISPATCH_KT(kt, __VA_ARGS__) }
+
+// launch `grid` CTAs in clusters of `cl` (cl == 1: a plain launch)
+template <class... KArgs, class... Args>
+static cudaError_t launch_chain_kernel(void (*kern)(KArgs...), int grid, int cl, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cl > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// number of gene-chains resident at once: CTAs per SM x SMs, or the clusters of `cl` CTAs the device can co-schedule
+template <class... KArgs>
+static int resident_chains(void (*kern)(KArgs...), int kt, int cl, size_t smem) {
+  const int ctas = sm_count() * ctas_per_sm(kt);
+  if (cl <= 1) return ctas;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ctas / cl * cl));
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = ctas / cl / 2;   // conservative: half of the slots
+  }
+  return std::max(1, std::min(n, ctas / cl));
+}
+
 extern "C" int32_t csplotch_log_prob_grad_dev(csplotch_batch *b, const double *theta_dev, const int32_t *gene_of_dev,
                                               int32_t Bn, double *lp_dev, double *grad_dev, int32_t jacobian,
                                               void *stream) {
@@ -946,13 +1103,16 @@ extern "C" int32_t csplotch_leapfrog_fixed(csplotch_batch *b, const double *thet
   k_to_internal<<<nb, 256>>>(stan, p, dm.imap, Bn, dm.D, dm.Di, 0.0);
   CU_TRY(cudaMemcpy(stan, inv_metric, nS * sizeof(double), cudaMemcpyHostToDevice));
   k_to_internal<<<nb, 256>>>(stan, mi, dm.imap, Bn, dm.D, dm.Di, 1.0);
-  const int grid = std::min(Bn, sm_count() * ctas_per_sm(m->kt));
   cudaError_t e = cudaSuccess;
-  DISPATCH_KT(m->kt, {
-    e = set_smem(k_leapfrog_fixed<KT>, m->smem_bytes);
-    if (e == cudaSuccess)
-      k_leapfrog_fixed<KT><<<grid, kBlock, m->smem_bytes>>>(dm, b->counts, b->pm, b->ps, b->lgam, b->nnz, b->G, q, p, g,
-                                                           mi, go, Bn, eps, n_steps, H);
+  const int cl = choose_cluster(m, Bn);
+  const DevModel dml = with_cluster(m, cl);
+  DISPATCH_KT_CL(m->kt, cl > 1, {
+    e = set_smem(k_leapfrog_fixed<KT, CLV>, m->smem_bytes);
+    if (e == cudaSuccess) {
+      const int grid = std::min(Bn, resident_chains(k_leapfrog_fixed<KT, CLV>, m->kt, cl, m->smem_bytes)) * cl;
+      e = launch_chain_kernel(k_leapfrog_fixed<KT, CLV>, grid, cl, m->smem_bytes, (cudaStream_t) nullptr, dml, b->counts,
+                              b->pm, b->ps, b->lgam, b->nnz, b->G, q, p, g, mi, go, Bn, eps, n_steps, H);
+    }
   });
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e));
@@ -998,18 +1158,22 @@ extern "C" int32_t csplotch_leapfrog_bench(csplotch_batch *b, int32_t Bn, double
   k_fill_hash<<<nb, 256>>>(p, nI, dm.imap, dm.Di, 2u, 2.0, 0.0);
   k_fill_hash<<<nb, 256>>>(mi, nI, dm.imap, dm.Di, 3u, 0.5, 1.0);
   CU_TRY(cudaMemset(g, 0, nI * sizeof(double)));
-  const int grid = std::min(Bn, sm_count() * ctas_per_sm(m->kt));
   cudaEvent_t e0, e1;
   CU_TRY(cudaEventCreate(&e0));
   CU_TRY(cudaEventCreate(&e1));
   cudaError_t e = cudaSuccess;
+  const int cl = choose_cluster(m, Bn);
+  const DevModel dml = with_cluster(m, cl);
   for (int r = 0; r <= reps && e == cudaSuccess; ++r) {
     if (r == 1) cudaEventRecord(e0);
-    DISPATCH_KT(m->kt, {
-      e = set_smem(k_leapfrog_fixed<KT>, m->smem_bytes);
-      if (e == cudaSuccess)
-        k_leapfrog_fixed<KT><<<grid, kBlock, m->smem_bytes>>>(dm, b->counts, b->pm, b->ps, b->lgam, b->nnz, b->G, q, p, g,
-                                                             mi, nullptr, Bn, eps, n_steps, H);
+    DISPATCH_KT_CL(m->kt, cl > 1, {
+      e = set_smem(k_leapfrog_fixed<KT, CLV>, m->smem_bytes);
+      if (e == cudaSuccess) {
+        const int grid = std::min(Bn, resident_chains(k_leapfrog_fixed<KT, CLV>, m->kt, cl, m->smem_bytes)) * cl;
+        e = launch_chain_kernel(k_leapfrog_fixed<KT, CLV>, grid, cl, m->smem_bytes, (cudaStream_t) nullptr, dml,
+                                b->counts, b->pm, b->ps, b->lgam, b->nnz, b->G, q, p, g, mi, (const int *)nullptr, Bn, eps,
+                                n_steps, H);
+      }
     });
     if (e == cudaSuccess) e = cudaGetLastError();
   }
@@ -1050,7 +1214,18 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   sd.cfg = NutsConfig{cfg->num_warmup, cfg->num_samples, cfg->max_depth, cfg->delta, cfg->gamma, cfg->kappa, cfg->t0,
                       cfg->init_buffer, cfg->term_buffer, cfg->window, cfg->init_radius, cfg->stepsize, cfg->seed};
   sd.counts = b->counts; sd.pm = b->pm; sd.ps = b->ps; sd.lgam = b->lgam; sd.nnz = b->nnz;
-  s->grid = std::min(W, sm_count() * ctas_per_sm(m->kt));
+  // gene-chains resident at once (CTAs, or clusters of s->cl CTAs)
+  s->cl = choose_cluster(m, W);
+  s->dml = with_cluster(m, s->cl);
+  {
+    int rc_chains = 0;
+    DISPATCH_KT_CL(m->kt, s->cl > 1, {
+      cudaError_t e0 = set_smem(k_nuts_advance<KT, CLV>, m->smem_bytes);
+      if (e0 != cudaSuccess) { delete s; return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e0)); }
+      rc_chains = resident_chains(k_nuts_advance<KT, CLV>, m->kt, s->cl, m->smem_bytes);
+    });
+    s->grid = std::min(W, rc_chains);
+  }
   sd.pool_vecs = 3 * cfg->max_depth + 8;
   const size_t Di = dm.Di, ns = (size_t)cfg->num_samples;
   // resident CTAs are also bounded by HBM: every CTA slot owns pool_vecs + 6 D-vectors of workspace
@@ -1085,7 +1260,7 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   A(&sd.queue, 1);
   A(&s->order_dev, (size_t)W);
   sd.order = s->order_dev;
-  A(&sd.slot_ns, (size_t)sd.n_slots);
+  A(&sd.slot_ns, (size_t)sd.n_slots * s->cl);
   if (e != cudaSuccess) {
     delete s;
     return fail(e == cudaErrorMemoryAllocation ? CSPLOTCH_E_NOMEM : CSPLOTCH_E_CUDA,
@@ -1160,9 +1335,11 @@ extern "C" int32_t csplotch_sampler_advance(csplotch_sampler *s, int32_t n_iter,
   CU_TRY(cudaMemsetAsync(s->sd.queue, 0, sizeof(int), s->stream));
   CU_TRY(cudaEventRecord(s->ev0, s->stream));
   cudaError_t e = cudaSuccess;
-  DISPATCH_KT(m->kt, {
-    e = set_smem(k_nuts_advance<KT>, m->smem_bytes);
-    if (e == cudaSuccess) k_nuts_advance<KT><<<s->grid, kBlock, m->smem_bytes, s->stream>>>(m->dm, s->sd, n_iter);
+  DISPATCH_KT_CL(m->kt, s->cl > 1, {
+    e = set_smem(k_nuts_advance<KT, CLV>, m->smem_bytes);
+    if (e == cudaSuccess)
+      e = launch_chain_kernel(k_nuts_advance<KT, CLV>, s->grid * s->cl, s->cl, m->smem_bytes, s->stream, s->dml, s->sd,
+                              n_iter);
   });
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e));
@@ -1221,14 +1398,22 @@ extern "C" int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out8) 
   return CSPLOTCH_OK;
 }
 
+extern "C" int32_t csplotch_sampler_layout(csplotch_sampler *s, int32_t *resident_chains_out, int32_t *cluster_size) {
+  if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
+  if (resident_chains_out) *resident_chains_out = s->sd.n_slots;
+  if (cluster_size) *cluster_size = s->cl;
+  return CSPLOTCH_OK;
+}
+
 // busy time of every resident CTA in the last launch: the spread between the mean and the maximum is the launch tail
 extern "C" int32_t csplotch_sampler_slot_ns(csplotch_sampler *s, int64_t *ns, int32_t cap, int32_t *n_slots) {
   if (!s || !n_slots) return fail(CSPLOTCH_E_INVALID, "null argument");
-  *n_slots = s->sd.n_slots;
+  const int n_ctas = s->sd.n_slots * s->cl;
+  *n_slots = n_ctas;
   if (ns) {
-    if (cap < s->sd.n_slots) return fail(CSPLOTCH_E_INVALID, "buffer too small");
+    if (cap < n_ctas) return fail(CSPLOTCH_E_INVALID, "buffer too small");
     CU_TRY(cudaStreamSynchronize(s->stream));
-    CU_TRY(cudaMemcpy(ns, s->sd.slot_ns, (size_t)s->sd.n_slots * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(ns, s->sd.slot_ns, (size_t)n_ctas * sizeof(long long), cudaMemcpyDeviceToHost));
   }
   return CSPLOTCH_OK;
 }
@@ -1267,6 +1452,18 @@ extern "C" int32_t csplotch_sampler_get_theta_draws(csplotch_sampler *s, double 
   const DevModel &dm = s->b->m->dm;
   CU_TRY(cudaStreamSynchronize(s->stream));
   CU_TRY(cudaMemcpy(theta, s->sd.theta, (size_t)s->sd.W * s->cfg.num_samples * dm.D * sizeof(double), cudaMemcpyDeviceToHost));
+  return CSPLOTCH_OK;
+}
+
+extern "C" int32_t csplotch_sampler_get_theta_draws_range(csplotch_sampler *s, int32_t g0, int32_t n_genes, double *theta) {
+  if (!s || !theta) return fail(CSPLOTCH_E_INVALID, "null argument");
+  if (!s->sd.theta) return fail(CSPLOTCH_E_INVALID, "sampler was created without keep_draws");
+  if (g0 < 0 || n_genes < 0 || g0 + n_genes > s->b->G) return fail(CSPLOTCH_E_INVALID, "gene range outside the batch");
+  const DevModel &dm = s->b->m->dm;
+  const size_t per_gene = (size_t)s->cfg.num_chains * s->cfg.num_samples * dm.D;
+  CU_TRY(cudaStreamSynchronize(s->stream));
+  if (n_genes)
+    CU_TRY(cudaMemcpy(theta, s->sd.theta + (size_t)g0 * per_gene, (size_t)n_genes * per_gene * sizeof(double), cudaMemcpyDeviceToHost));
   return CSPLOTCH_OK;
 }
 
@@ -1374,7 +1571,7 @@ k_write_array(const __grid_constant__ DevModel m_in, const double *__restrict__ 
     double *oll = o + m.D;
     const double sig03 = 0.3 * sc.sigma;
     for (int j = threadIdx.x; j < m.N; j += kBlock) {
-      const double *bj = ops.B + (m.bot0 * m.C) * m.K + (m.key[j] & 0xFFFFFF) * m.K;
+      const double *bj = ops.Bs() + (m.bot0 * m.C) * m.K + (m.key[j] & 0xFFFFFF) * m.K;
       double ll = 0.0;
       if (KT == 1) ll = bj[0];
       else {
@@ -1396,7 +1593,7 @@ k_write_array(const __grid_constant__ DevModel m_in, const double *__restrict__ 
       if (i < m.L1) { lev0 = 0; nr = m.L1; off = 0; }
       else if (i < m.L1 + m.L2) { lev0 = m.L1; nr = m.L2; off = m.L1 * CKt; }
       else { lev0 = m.L1 + m.L2; nr = m.L3; off = (m.L1 + m.L2) * CKt; }
-      ob[off + (i - lev0) + nr * (j + m.C * k)] = ops.B[idx];
+      ob[off + (i - lev0) + nr * (j + m.C * k)] = ops.Bs()[idx];
     }
     __syncthreads();
   }

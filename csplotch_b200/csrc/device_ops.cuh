@@ -15,6 +15,7 @@
 // Internal vector layout (all vectors of a chain, HBM):  [ psi(Npad) | noise(Npad) | small ]
 // small = beta_raw[(i*C+j)*K+k] | tau | a | sigma | sigma_level_2 | sigma_level_3 | theta.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,7 +26,7 @@ namespace csp {
 
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
-constexpr int kRedMax = 12;  // doubles per block reduction
+constexpr int kRedMax = 16;  // doubles per block reduction
 constexpr int kTile = kBlock;    // spots per tile of the staged pipeline: thread t <-> spot t of the tile
 constexpr int kMaxEll = 8;       // widest ELL adjacency the tiled path takes (Visium hex: 6, ST / HD grid: 4)
 // The CAR log-determinant sum_i m_i log(1 - a lambda_i) and its derivative in a, -sum_i m_i lambda_i / (1 - a lambda_i),
@@ -88,7 +89,15 @@ struct DevModel {
   const int *map2;       // [L2] 0-based level-1 row of each level-2 row
   const int *map3;       // [L3] 0-based level-2 row of each level-3 row
   const int *imap;       // [Di] internal index -> Stan index (-1 = padding)
+  // ---- one gene-chain per thread-block CLUSTER (cl > 1: long designs; the sampler and the trajectory kernels) ----
+  // Rank r of the cluster evaluates tiles [cl_t0[r], cl_t0[r+1]) and owns the same element ranges of every D-vector
+  // (rank 0 also the small block, and fewer tiles for it); psi of the `look` tiles either side of a rank's range is
+  // drifted redundantly into halo cells behind the ring, which the cluster's own ELL table addresses.
+  int cl;                // CTAs per gene-chain: 1, 2, 4 or 8
+  int cl_t0[9];          // tile boundaries of the ranks
+  const unsigned short *ell_cl;  // [NT][ell_w][kTile] like ell, neighbours outside the owner's tile range -> halo cells
 };
+constexpr int kMaxCluster = 8;
 
 struct GeneDev {
   const int *counts;   // [N] internal spot order
@@ -279,14 +288,34 @@ struct TmaDesc {
 };
 constexpr int kMaxDesc = 12;
 
-template <int KT>
+namespace cg = cooperative_groups;
+
+// CL: one gene-chain per thread-block cluster (every collective below then spans the cluster: element loops run
+// over this rank's ranges, reductions are combined through distributed shared memory in rank order, so every CTA of
+// the cluster holds bitwise identical scalars and executes the same control flow)
+template <int KT, bool CL = false>
 struct DevOps {
   const DevModel &m;
+  // cluster geometry of this CTA (CL only; otherwise rank 0 of 1 with the whole tile range)
+  int crank = 0, csize = 1, ta = 0, tb = 0;
+  int nseg = 1, seg_lo[3] = {0, 0, 0}, seg_hi[3] = {0, 0, 0};   // element ranges of a D-vector this CTA owns
+  double *cl_part = nullptr;   // [16] this CTA's partial sums of finish()            (shared memory, read by rank 0)
+  double *cl_bcast = nullptr;  // [4]  rank 0's results of finish(): V, K, finite, pp  (read by the other ranks)
+  double *cl_red = nullptr;    // [2][8] partial sums of the all-to-all reductions, double buffered
+  double *cl_sc = nullptr;     // [12] the constrained scalars of the evaluation in flight (finish_small, warp 0)
+  double *halo = nullptr;      // [2][look * kTile] drifted psi of the tiles below / above this rank's range
+  int cl_par = 0;
   GeneDev gn;
   RngKey key;
   int jacobian;
   // shared memory: B[nbeta] | adjB[nbeta] | red[kWarps*kRedMax] | mbar[kStages] | ring[4 T] | phr[2 T] | stages
-  double *B, *adjB, *red;
+  // offsets (in doubles) into the one dynamic shared-memory array: going through smem_d + offset (instead of generic
+  // pointers kept in this object, which lives in local memory) lets ptxas emit LDS / STS / ATOMS with 32-bit addresses
+  int B_o = 0, adjB_o = 0, red_o = 0, sraw_o = 0;
+  __device__ __forceinline__ double *Bs() const { return smem_d + B_o; }
+  __device__ __forceinline__ double *As() const { return smem_d + adjB_o; }
+  __device__ __forceinline__ double *Rs() const { return smem_d + red_o; }
+  __device__ __forceinline__ double *Ss() const { return smem_d + sraw_o; }
   uint64_t *mbar;        // [0..3] psi slot landed (TMA), [4,5] rest slot landed (TMA), [6,7] psi of a tile is in the
                          // ring (256 arrivals), [8,9] every thread is done with a tile's staged inputs (256 arrivals)
   double *ring;          // drifted psi of tiles k-1, k, k+1 (+1 spare): ring[j & (4 T - 1)]
@@ -320,66 +349,130 @@ struct DevOps {
 #define PWSTART() {}
 #endif
 
-  __device__ __forceinline__ DevOps(const DevModel &mm) : m(mm) {}
+  __device__ __forceinline__ DevOps(const DevModel &mm) : m(mm) {
+    tb = mm.NT;
+    seg_hi[0] = mm.Di;
+  }
+  // bind this CTA to its rank of the cluster (CL kernels, after the model descriptor is staged)
+  __device__ __forceinline__ void bind_cluster() {
+    if (!CL) return;
+    cg::cluster_group cluster = cg::this_cluster();
+    crank = (int)cluster.block_rank();
+    csize = (int)cluster.num_blocks();
+    ta = m.cl_t0[crank];
+    tb = m.cl_t0[crank + 1];
+    nseg = 0;
+    if (m.car) { seg_lo[nseg] = m.o_psi + ta * kTile; seg_hi[nseg] = m.o_psi + tb * kTile; ++nseg; }
+    seg_lo[nseg] = m.o_noise + ta * kTile; seg_hi[nseg] = m.o_noise + tb * kTile; ++nseg;
+    if (crank == 0) { seg_lo[nseg] = m.o_small; seg_hi[nseg] = m.Di; ++nseg; }
+  }
+  __device__ __forceinline__ void cluster_sync() {
+    if (CL) cg::this_cluster().sync();
+  }
+  template <class T>
+  __device__ __forceinline__ T *remote(T *p, int rank) const {
+    return cg::this_cluster().map_shared_rank(p, (unsigned)rank);
+  }
+  // sum of NV values over the whole gene-chain (CTA, or every CTA of the cluster in rank order): identical in
+  // every thread of every CTA
+  template <int NV>
+  __device__ __forceinline__ void chain_sum(double (&v)[NV]) {
+    block_sum<NV>(v, Rs());
+    if (!CL) return;
+    static_assert(NV <= 8, "cl_red holds 8 values per buffer");
+    double *buf = cl_red + 8 * cl_par;
+    cl_par ^= 1;
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) buf[i] = v[i];
+    }
+    cluster_sync();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = 0.0;
+    for (int r = 0; r < csize; ++r) {
+      const double *rb = remote(buf, r);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] += rb[i];
+    }
+  }
 
   __device__ __forceinline__ double *vec(int id) const { return pool + (size_t)id * m.Di; }
 
   // ---- constrained scalars + beta levels into shared memory --------------------------------
-  __device__ __forceinline__ void load_small(const double *q, Scalars &sc) {
+  // Two steps: the unconstrained small block is first STAGED in shared memory (beta_raw in Bs()[], the scalars in Ss()[]:
+  // by stage_small() from a vector in HBM, or directly by the leapfrog prologue, which has the drifted values in
+  // registers), then finish_small() turns it in place into the constrained scalars and the beta levels.  No element of
+  // the small block is fetched from HBM more than once per evaluation, and every fetch is one of a batch of
+  // independent loads (a dependent global load per loop trip cost a full L2 round trip each: a third of a c2 evaluation).
+  static constexpr int kUB = 4;   // elements per thread and batch
+  __device__ __forceinline__ void stage_small(const double *q) {
     const double *sb = q + m.o_small;
-    const double *ss = sb + m.nbeta;
-    sc.tau = sc.a = sc.s2 = sc.s3 = sc.theta = 0.0;
-    double jac = 0.0;
-    // all (<= 6) unconstrained scalars in ONE batch of independent loads: fetched one by one inside the
-    // branches below, each paid a full L2 round trip before its exp()
+    for (int i0 = threadIdx.x; i0 < m.nsmall; i0 += kUB * kBlock) {
+      double v[kUB];
+#pragma unroll
+      for (int u = 0; u < kUB; ++u) {
+        const int i = i0 + u * kBlock;
+        v[u] = i < m.nsmall ? sb[i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kUB; ++u) {
+        const int i = i0 + u * kBlock;
+        if (i < m.nbeta) Bs()[i] = v[u];
+        else if (i < m.nsmall) Ss()[i - m.nbeta] = v[u];
+      }
+    }
+  }
+  __device__ __forceinline__ void finish_small(Scalars &sc) {
+    // The constrained scalars: exp / logit of <= 7 numbers, ~700 fp64 instructions when one thread does them all.
+    // Seven lanes of warp 0 take one scalar each and publish value, logs and log-Jacobian term through shared memory
+    // (cl_sc) while the other warps start on the beta levels; everybody picks the results up after the first barrier.
     const int last = m.nscal - 1;
-    const double u_tau = ss[max(0, min(m.s_tau, last))], u_a = ss[max(0, min(m.s_a, last))];
-    const double u_sigma = ss[m.s_sigma], u_s2 = ss[max(0, min(m.s_s2, last))];
-    const double u_s3 = ss[max(0, min(m.s_s3, last))], u_theta = ss[max(0, min(m.s_theta, last))];
-    const double u_phi = ss[max(0, min(m.s_phi, last))];
-    sc.log_tau = 0.0;
-    sc.log1m_theta = 0.0;
-    if (m.car) {
-      sc.tau = exp(u_tau);
-      sc.log_tau = u_tau;
-      jac += u_tau;
-      double la, l1a;
-      logit_triple(u_a, sc.a, la, l1a);
-      jac += la + l1a;
+    if (threadIdx.x < 8) {
+      const int t = threadIdx.x;
+      double *o = cl_sc;   // [0..5] tau a sigma s2 s3 theta | [6] jac | [7] log_tau | [8] log1m_theta | [9] log_theta | [10] phi | [11] log_phi
+      double val = 0.0, jt = 0.0, e1 = 0.0, e2 = 0.0;
+      if (t == 0 && m.car) { const double u = Ss()[max(0, min(m.s_tau, last))]; val = exp(u); jt = u; e1 = u; }
+      if (t == 1 && m.car) { const double u = Ss()[max(0, min(m.s_a, last))]; double la, l1a; logit_triple(u, val, la, l1a); jt = la + l1a; }
+      if (t == 2) { const double u = Ss()[m.s_sigma]; val = exp(u); jt = u; }
+      if (t == 3 && m.L2) { const double u = Ss()[max(0, min(m.s_s2, last))]; val = exp(u); jt = u; }
+      if (t == 4 && m.L3) { const double u = Ss()[max(0, min(m.s_s3, last))]; val = exp(u); jt = u; }
+      if (t == 5 && m.zi) { const double u = Ss()[max(0, min(m.s_theta, last))]; logit_triple(u, val, e2, e1); jt = e2 + e1; }
+      if (t == 6 && m.nb) { const double u = Ss()[max(0, min(m.s_phi, last))]; val = 1e-6 + exp(u); e1 = log(val); jt = u; }
+      // log-Jacobian in declaration order: tau, a, sigma, sigma_level_2, sigma_level_3, theta, phi
+      double jac = 0.0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) jac += __shfl_sync(0xffu, jt, k);
+      if (t < 6) o[t] = val;
+      if (t == 0) { o[6] = jacobian ? jac : 0.0; o[7] = e1; }
+      if (t == 5) { o[8] = e1; o[9] = e2; }
+      if (t == 6) { o[10] = val; o[11] = e1; }
     }
-    sc.sigma = exp(u_sigma);
-    jac += u_sigma;
-    if (m.L2) { sc.s2 = exp(u_s2); jac += u_s2; }
-    if (m.L3) { sc.s3 = exp(u_s3); jac += u_s3; }
-    sc.log_theta = 0.0;
-    if (m.zi) {
-      logit_triple(u_theta, sc.theta, sc.log_theta, sc.log1m_theta);
-      jac += sc.log_theta + sc.log1m_theta;
-    }
-    sc.phi = sc.log_phi = 0.0;
-    if (m.nb) {
-      sc.phi = 1e-6 + exp(u_phi);
-      sc.log_phi = log(sc.phi);
-      jac += u_phi;
-    }
-    sc.jac = jacobian ? jac : 0.0;
+    // beta levels in place: Bs()[idx] holds beta_raw on entry
     const int CK = m.C * m.K;
     for (int idx = threadIdx.x; idx < m.L1 * CK; idx += kBlock) {
-      const double r = sb[idx];
-      B[idx] = (m.family == 1) ? r * gn.ps[idx % m.K] + gn.pm[idx % m.K] : 2.0 * r;
+      const double r = Bs()[idx];
+      Bs()[idx] = (m.family == 1) ? r * gn.ps[idx % m.K] + gn.pm[idx % m.K] : 2.0 * r;
     }
     __syncthreads();
+    sc.tau = cl_sc[0]; sc.a = cl_sc[1]; sc.sigma = cl_sc[2]; sc.s2 = cl_sc[3]; sc.s3 = cl_sc[4]; sc.theta = cl_sc[5];
+    sc.jac = cl_sc[6]; sc.log_tau = cl_sc[7]; sc.log1m_theta = cl_sc[8]; sc.log_theta = cl_sc[9]; sc.phi = cl_sc[10];
+    sc.log_phi = cl_sc[11];
     for (int idx = threadIdx.x; idx < m.L2 * CK; idx += kBlock) {
       const int i = idx / CK, rem = idx - i * CK;
-      B[(m.L1 + i) * CK + rem] = B[m.map2[i] * CK + rem] + sc.s2 * sb[(m.L1 + i) * CK + rem];
+      Bs()[(m.L1 + i) * CK + rem] = Bs()[m.map2[i] * CK + rem] + sc.s2 * Bs()[(m.L1 + i) * CK + rem];
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < m.L3 * CK; idx += kBlock) {
       const int i = idx / CK, rem = idx - i * CK;
-      B[(m.L1 + m.L2 + i) * CK + rem] =
-          B[(m.L1 + m.map3[i]) * CK + rem] + sc.s3 * sb[(m.L1 + m.L2 + i) * CK + rem];
+      Bs()[(m.L1 + m.L2 + i) * CK + rem] =
+          Bs()[(m.L1 + m.map3[i]) * CK + rem] + sc.s3 * Bs()[(m.L1 + m.L2 + i) * CK + rem];
     }
     __syncthreads();
+  }
+  __device__ __forceinline__ void load_small(const double *q, Scalars &sc) {
+    stage_small(q);
+    __syncthreads();
+    finish_small(sc);
   }
 
   // warp-collective flush of the per-lane bottom-level bins into adjB (shared)
@@ -395,7 +488,7 @@ struct DevOps {
       for (int k = 0; k < KT; ++k) {
         if (k < m.K) {
           const double s = warp_sum(mine ? acc[k] : 0.0);
-          if (lane == leader) atomicAdd(&adjB[(m.bot0 * m.C) * m.K + k0 * m.K + k], s);
+          if (lane == leader) atomicAdd(&As()[(m.bot0 * m.C) * m.K + k0 * m.K + k], s);
         }
       }
       remaining &= ~same;
@@ -421,9 +514,10 @@ struct DevOps {
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
       const int e = so + max(0, sidx[s]);
-      ph_s[s] = LEAP ? dp[e] : 0.0;
-      mi_s[s] = LEAP ? minv[e] : 0.0;
-      po_s[s] = (LEAP && rho_out) ? sp[e] : 0.0;
+      const bool w0 = tid < 32;   // only warp 0 runs the scalar epilogue
+      ph_s[s] = (LEAP && w0) ? dp[e] : 0.0;
+      mi_s[s] = (LEAP && w0) ? minv[e] : 0.0;
+      po_s[s] = (LEAP && w0 && rho_out) ? sp[e] : 0.0;
     }
     // log-determinant term of the CAR prior over the distinct eigenvalues (the tiled pass folds it into
     // its tile loop, where it is independent work that fills stall slots)
@@ -431,125 +525,165 @@ struct DevOps {
       for (int i = tid; i < m.n_eigg; i += kBlock)
         eig_group_terms(m.eigg + (size_t)i * kEigGroup, __ldg(m.eiggm + i), sc.a, a_ldet, a_dldet);
     }
-    // beta_raw ~ normal(0,1)
-    const double *sb = dq + m.o_small;
-    for (int idx = tid; idx < m.nbeta; idx += kBlock) a_lp -= 0.5 * sb[idx] * sb[idx];
-
-    double r1[10] = {a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_ldet, a_dldet, a_g2, a_dphi};
-    block_sum<10>(r1, red);  // also orders the shared atomics on adjB before the reads below
+    __syncthreads();  // the shared atomics on adjB of every warp are done
 
     // reverse of the hierarchy (A.3): parents collect their children
     const int CK = m.C * m.K;
     if (m.L3) {
       for (int idx = tid; idx < m.L2 * CK; idx += kBlock) {
         const int i2 = idx / CK, rem = idx - i2 * CK;
-        double s = adjB[(m.L1 + i2) * CK + rem];
+        double s = As()[(m.L1 + i2) * CK + rem];
         for (int i3 = 0; i3 < m.L3; ++i3)
-          if (m.map3[i3] == i2) s += adjB[(m.L1 + m.L2 + i3) * CK + rem];
-        adjB[(m.L1 + i2) * CK + rem] = s;
+          if (m.map3[i3] == i2) s += As()[(m.L1 + m.L2 + i3) * CK + rem];
+        As()[(m.L1 + i2) * CK + rem] = s;
       }
       __syncthreads();
     }
     if (m.L2) {
       for (int idx = tid; idx < m.L1 * CK; idx += kBlock) {
         const int i1 = idx / CK, rem = idx - i1 * CK;
-        double s = adjB[i1 * CK + rem];
+        double s = As()[i1 * CK + rem];
         for (int i2 = 0; i2 < m.L2; ++i2)
-          if (m.map2[i2] == i1) s += adjB[(m.L1 + i2) * CK + rem];
-        adjB[i1 * CK + rem] = s;
+          if (m.map2[i2] == i1) s += As()[(m.L1 + i2) * CK + rem];
+        As()[i1 * CK + rem] = s;
       }
       __syncthreads();
     }
-    double a_ds2 = 0, a_ds3 = 0, a_kin2 = 0, a_g2b = 0;
-    for (int idx = tid; idx < m.nbeta; idx += kBlock) {
-      const int i = idx / CK;
-      const double ab = adjB[idx], r = sb[idx];
-      double scale;
-      if (i < m.L1) scale = (m.family == 1) ? gn.ps[idx % m.K] : 2.0;
-      else if (i < m.L1 + m.L2) { scale = sc.s2; a_ds2 += ab * r; }
-      else { scale = sc.s3; a_ds3 += ab * r; }
-      const double gr = scale * ab - r;
-      dg[m.o_small + idx] = -gr;
-      a_g2b += gr * gr;
-      if (LEAP) {
-        const double pn = dp[m.o_small + idx] + 0.5 * eps * gr;
-        dp[m.o_small + idx] = pn;
-        a_kin2 += minv[m.o_small + idx] * pn * pn;
-        if (rho_out) {
-          const double po = sp[m.o_small + idx];
-          a_pp += minv[m.o_small + idx] * po * pn;
-          rho_out[m.o_small + idx] = po + pn;
-        }
-      }
-    }
-    double r2[5] = {a_ds2, a_ds3, a_kin2, a_g2b, a_pp};
-    block_sum<5>(r2, red);
-
-    // scalars: every thread computes them (uniform), thread 0 stores
-    double lp = r1[0] + sc.jac;
-    double kin = r1[5] + r2[2];
-    double g2 = r1[8] + r2[3];
-    double gu_tau = 0, gu_a = 0, gu_sigma, gu_s2 = 0, gu_s3 = 0, gu_theta = 0, gu_phi = 0;
-    if (m.car) {
-      const double Q = r1[2] - sc.a * r1[3];
-      const double inv_tau = 1.0 / sc.tau;
-      lp += -2.0 * sc.log_tau - inv_tau;
-      lp += 0.5 * ((double)m.N * sc.log_tau + r1[6] - sc.tau * Q);
-      const double d_tau = -2.0 * inv_tau + inv_tau * inv_tau + 0.5 * ((double)m.N * inv_tau - Q);
-      const double d_a = 0.5 * (r1[7] + sc.tau * r1[3]);
-      gu_tau = sc.tau * d_tau + (jacobian ? 1.0 : 0.0);
-      gu_a = sc.a * (1.0 - sc.a) * d_a + (jacobian ? (1.0 - 2.0 * sc.a) : 0.0);
-    }
-    lp += -0.5 * sc.sigma * sc.sigma;
-    gu_sigma = sc.sigma * (-sc.sigma + 0.3 * r1[1]) + (jacobian ? 1.0 : 0.0);
-    if (m.L2) { lp += -0.5 * sc.s2 * sc.s2; gu_s2 = sc.s2 * (-sc.s2 + r2[0]) + (jacobian ? 1.0 : 0.0); }
-    if (m.L3) { lp += -0.5 * sc.s3 * sc.s3; gu_s3 = sc.s3 * (-sc.s3 + r2[1]) + (jacobian ? 1.0 : 0.0); }
-    if (m.zi) {
-      lp += tails;                      // theta ~ beta(1,2)
-      lp += gn.nnz * tails - (m.nb ? 0.0 : gn.lgam);  // bernoulli(0|theta) and -lgamma(y+1) of the non-zero spots
-      const double d_theta = r1[4] - (gn.nnz + 1.0) / (1.0 - sc.theta);
-      gu_theta = sc.theta * (1.0 - sc.theta) * d_theta + (jacobian ? (1.0 - 2.0 * sc.theta) : 0.0);
-    }
-    if (m.nb) {
-      lp += sc.log_phi - sc.phi;  // phi ~ gamma(2,1)
-      gu_phi = (sc.phi - 1e-6) * (r1[9] + 1.0 / sc.phi - 1.0) + (jacobian ? 1.0 : 0.0);
-    }
-    // read phase (all threads) then write phase (thread 0) of the scalar momenta
-    double pn_s[7] = {0, 0, 0, 0, 0, 0, 0};
-    double pp = r2[4];
-    const double gu[7] = {gu_tau, gu_a, gu_sigma, gu_s2, gu_s3, gu_theta, gu_phi};
+    // beta_raw: prior normal(0,1), gradient, second half-kick (and the fused level-0 merge) — batches of independent loads
+    const double *sb = dq + m.o_small;
+    double a_ds2 = 0, a_ds3 = 0;
+    for (int i0 = tid; i0 < m.nbeta; i0 += kUB * kBlock) {
+      double rv[kUB], pv[kUB], wv[kUB], ov[kUB];
 #pragma unroll
-    for (int s = 0; s < 7; ++s) {
-      if (sidx[s] >= 0) {
-        g2 += gu[s] * gu[s];
-        if (LEAP) {
-          pn_s[s] = ph_s[s] + 0.5 * eps * gu[s];
-          kin += mi_s[s] * pn_s[s] * pn_s[s];
-          if (rho_out) pp += mi_s[s] * po_s[s] * pn_s[s];
+      for (int u = 0; u < kUB; ++u) {
+        const int idx = i0 + u * kBlock;
+        const bool in = idx < m.nbeta;
+        rv[u] = in ? sb[idx] : 0.0;
+        pv[u] = (LEAP && in) ? dp[m.o_small + idx] : 0.0;
+        wv[u] = (LEAP && in) ? minv[m.o_small + idx] : 0.0;
+        ov[u] = (LEAP && in && rho_out) ? sp[m.o_small + idx] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kUB; ++u) {
+        const int idx = i0 + u * kBlock;
+        if (idx < m.nbeta) {
+          const int i = idx / CK;
+          const double ab = As()[idx], r = rv[u];
+          a_lp -= 0.5 * r * r;
+          double scale;
+          if (i < m.L1) scale = (m.family == 1) ? gn.ps[idx % m.K] : 2.0;
+          else if (i < m.L1 + m.L2) { scale = sc.s2; a_ds2 += ab * r; }
+          else { scale = sc.s3; a_ds3 += ab * r; }
+          const double gr = scale * ab - r;
+          dg[m.o_small + idx] = -gr;
+          a_g2 += gr * gr;
+          if (LEAP) {
+            const double pn = pv[u] + 0.5 * eps * gr;
+            dp[m.o_small + idx] = pn;
+            a_kin += wv[u] * pn * pn;
+            if (rho_out) {
+              a_pp += wv[u] * ov[u] * pn;
+              rho_out[m.o_small + idx] = ov[u] + pn;
+            }
+          }
         }
       }
     }
-    __syncthreads();
-    if (tid == 0) {
+    // ONE block reduction for everything the spot loop and this epilogue accumulated, finished by warp 0 alone:
+    // the scalar epilogue below is a few hundred fp64 instructions (divisions included) with CTA-uniform operands —
+    // executed by all eight warps it was a sixth of a c2 evaluation's instructions.  Warp 0 computes, the four results
+    // go through shared memory.
+    constexpr int NR = 13;
+    double r1[NR] = {a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_ldet, a_dldet, a_g2, a_dphi, a_ds2, a_ds3, a_pp};
+    {
+      const int lane = tid & 31, warp = tid >> 5;
+      double *red = Rs();
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const double sw = warp_sum(r1[i]);
+        if (lane == 0) red[warp * kRedMax + i] = sw;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        double tot = 0.0;
+        if (lane < NR) {
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) tot += red[w * kRedMax + lane];
+        }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) r1[i] = __shfl_sync(0xffffffffu, tot, i);
+      }
+    }
+    if (tid < 32) {
+      const double r2[5] = {r1[10], r1[11], 0.0, 0.0, r1[12]};
+      double lp = r1[0] + sc.jac;
+      double kin = r1[5];
+      double g2 = r1[8];
+      double gu_tau = 0, gu_a = 0, gu_sigma, gu_s2 = 0, gu_s3 = 0, gu_theta = 0, gu_phi = 0;
+      if (m.car) {
+        const double Q = r1[2] - sc.a * r1[3];
+        const double inv_tau = 1.0 / sc.tau;
+        lp += -2.0 * sc.log_tau - inv_tau;
+        lp += 0.5 * ((double)m.N * sc.log_tau + r1[6] - sc.tau * Q);
+        const double d_tau = -2.0 * inv_tau + inv_tau * inv_tau + 0.5 * ((double)m.N * inv_tau - Q);
+        const double d_a = 0.5 * (r1[7] + sc.tau * r1[3]);
+        gu_tau = sc.tau * d_tau + (jacobian ? 1.0 : 0.0);
+        gu_a = sc.a * (1.0 - sc.a) * d_a + (jacobian ? (1.0 - 2.0 * sc.a) : 0.0);
+      }
+      lp += -0.5 * sc.sigma * sc.sigma;
+      gu_sigma = sc.sigma * (-sc.sigma + 0.3 * r1[1]) + (jacobian ? 1.0 : 0.0);
+      if (m.L2) { lp += -0.5 * sc.s2 * sc.s2; gu_s2 = sc.s2 * (-sc.s2 + r2[0]) + (jacobian ? 1.0 : 0.0); }
+      if (m.L3) { lp += -0.5 * sc.s3 * sc.s3; gu_s3 = sc.s3 * (-sc.s3 + r2[1]) + (jacobian ? 1.0 : 0.0); }
+      if (m.zi) {
+        lp += tails;                      // theta ~ beta(1,2)
+        lp += gn.nnz * tails - (m.nb ? 0.0 : gn.lgam);  // bernoulli(0|theta) and -lgamma(y+1) of the non-zero spots
+        const double d_theta = r1[4] - (gn.nnz + 1.0) / (1.0 - sc.theta);
+        gu_theta = sc.theta * (1.0 - sc.theta) * d_theta + (jacobian ? (1.0 - 2.0 * sc.theta) : 0.0);
+      }
+      if (m.nb) {
+        lp += sc.log_phi - sc.phi;  // phi ~ gamma(2,1)
+        gu_phi = (sc.phi - 1e-6) * (r1[9] + 1.0 / sc.phi - 1.0) + (jacobian ? 1.0 : 0.0);
+      }
+      double pn_s[7] = {0, 0, 0, 0, 0, 0, 0};
+      double pp = r2[4];
+      const double gu[7] = {gu_tau, gu_a, gu_sigma, gu_s2, gu_s3, gu_theta, gu_phi};
 #pragma unroll
       for (int s = 0; s < 7; ++s) {
         if (sidx[s] >= 0) {
-          dg[so + sidx[s]] = -gu[s];
-          if (LEAP) dp[so + sidx[s]] = pn_s[s];
-          if (LEAP && rho_out) rho_out[so + sidx[s]] = po_s[s] + pn_s[s];
+          g2 += gu[s] * gu[s];
+          if (LEAP) {
+            pn_s[s] = ph_s[s] + 0.5 * eps * gu[s];
+            kin += mi_s[s] * pn_s[s] * pn_s[s];
+            if (rho_out) pp += mi_s[s] * po_s[s] * pn_s[s];
+          }
         }
       }
-      for (int s = m.nsmall; s < m.nsmall_pad; ++s) {
-        dg[m.o_small + s] = 0.0;
-        if (LEAP) dp[m.o_small + s] = 0.0;
-        if (LEAP && rho_out) rho_out[m.o_small + s] = 0.0;
+      if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+          if (sidx[s] >= 0) {
+            dg[so + sidx[s]] = -gu[s];
+            if (LEAP) dp[so + sidx[s]] = pn_s[s];
+            if (LEAP && rho_out) rho_out[so + sidx[s]] = po_s[s] + pn_s[s];
+          }
+        }
+        for (int s = m.nsmall; s < m.nsmall_pad; ++s) {
+          dg[m.o_small + s] = 0.0;
+          if (LEAP) dp[m.o_small + s] = 0.0;
+          if (LEAP && rho_out) rho_out[m.o_small + s] = 0.0;
+        }
+        cl_bcast[0] = -lp;
+        cl_bcast[1] = 0.5 * kin;
+        cl_bcast[2] = (isfinite(lp) && isfinite(g2)) ? 1.0 : 0.0;
+        cl_bcast[3] = pp;
       }
     }
     __syncthreads();
-    if (pp_out) *pp_out = pp;
-    if (V_out) *V_out = -lp;
-    if (K_out) *K_out = 0.5 * kin;
-    if (finite_out) *finite_out = isfinite(lp) && isfinite(g2);
+    if (pp_out) *pp_out = cl_bcast[3];
+    if (V_out) *V_out = cl_bcast[0];
+    if (K_out) *K_out = cl_bcast[1];
+    if (finite_out) *finite_out = cl_bcast[2] != 0.0;
+    __syncthreads();   // cl_bcast may be rewritten by the next evaluation only after everyone has read it
   }
 
 
@@ -565,7 +699,7 @@ struct DevOps {
   // local memory (the functions are __noinline__), so member / model-field accesses inside the loop would
   // be dependent generic loads on the critical path.
   struct TileCtx {
-    int NT, ell_w, car, zi, o_psi, o_noise, stage_bytes, n_desc;
+    int NT, ta, ell_w, car, zi, o_psi, o_noise, stage_bytes, n_desc;   // NT: tiles of THIS CTA, the first is tile ta
     uint32_t seq0, psi_tx, rest_tx;
     const double *E;
     int ring_o, psi_o, rest_o, Bbot_o, bins_o;  // offsets (in doubles) into smem_d
@@ -575,14 +709,14 @@ struct DevOps {
   template <bool LEAP>
   __device__ __forceinline__ TileCtx make_ctx(const double *sq, const double *sg, const double *sp) {
     TileCtx c;
-    c.NT = m.NT; c.ell_w = m.ell_w; c.car = m.car; c.zi = m.zi;
+    c.NT = tb - ta; c.ta = ta; c.ell_w = m.ell_w; c.car = m.car; c.zi = m.zi;
     c.o_psi = m.o_psi; c.o_noise = m.o_noise; c.stage_bytes = m.stage_bytes;
     const int bin0 = (m.bot0 * m.C) * KT;
     c.seq0 = tile_seq;
     c.E = m.E;
     c.ring_o = (int)(ring - smem_d); c.psi_o = (int)(psi_st - smem_d);
     c.rest_o = (int)(reinterpret_cast<double *>(rest_st) - smem_d);
-    c.Bbot_o = (int)(B - smem_d) + bin0; c.bins_o = (int)(adjB - smem_d) + bin0;
+    c.Bbot_o = B_o + bin0; c.bins_o = adjB_o + bin0;
     c.mbar = mbar;
     c.desc = tdesc;
     constexpr uint32_t vb = kTile * sizeof(double), ib = kTile * sizeof(int);
@@ -615,7 +749,7 @@ struct DevOps {
         } else if (r == nv + 2) {
           d.src = reinterpret_cast<const unsigned char *>(m.key); d.tile_bytes = ib; d.dst_off = 5 * vb + ib;
         } else {
-          d.src = reinterpret_cast<const unsigned char *>(m.ell); d.tile_bytes = (uint32_t)m.ell_w * (ib / 2);
+          d.src = reinterpret_cast<const unsigned char *>((CL && csize > 1) ? m.ell_cl : m.ell); d.tile_bytes = (uint32_t)m.ell_w * (ib / 2);
           d.dst_off = 5 * vb + 2 * ib;
         }
       }
@@ -638,7 +772,7 @@ struct DevOps {
       unsigned char *dst = d.group == 0
                                ? reinterpret_cast<unsigned char *>(smem_d + c.psi_o) + slot * (4 * kTile * sizeof(double))
                                : reinterpret_cast<unsigned char *>(smem_d + c.rest_o) + (size_t)slot * c.stage_bytes;
-      bulk_g2s(dst + d.dst_off, d.src + (size_t)tile * d.tile_bytes, d.tile_bytes, c.mbar + 4 * d.group + slot);
+      bulk_g2s(dst + d.dst_off, d.src + (size_t)(c.ta + tile) * d.tile_bytes, d.tile_bytes, c.mbar + 4 * d.group + slot);
     }
   }
   template <int LOOK>
@@ -672,7 +806,7 @@ struct DevOps {
     const double *d = smem_d + c.psi_o + ps * 4 * kTile;
     double qn = d[t];
     if (LEAP) qn += eps * d[3 * kTile + t] * (d[kTile + t] - 0.5 * eps * d[2 * kTile + t]);
-    smem_d[c.ring_o + ((k * kTile + t) & RMASK)] = qn;
+    smem_d[c.ring_o + (((c.ta + k) * kTile + t) & RMASK)] = qn;
     mbar_arrive_cta(c.mbar + 6 + (seq & 1u));  // "psi of tile k is in the ring"
   }
 
@@ -751,20 +885,69 @@ struct DevOps {
     // the first tiles start streaming while the small block is prepared
     if (tid < 32)
       for (int k0 = -(LOOK + 1); k0 < 0; ++k0) issue_tiles<LOOK>(c, k0);  // psi(0..look), rest(0)
-    // small block: half-kick + drift (or copy), then constrained scalars and beta levels
-    for (int e = m.o_small + tid; e < m.Di; e += kBlock) {
-      double qn = sq[e];
-      if (LEAP) {
-        const double ph = sp[e] - 0.5 * eps * sg[e];
-        qn += eps * minv[e] * ph;
-        dp[e] = ph;
+    const bool clustered = CL && csize > 1;
+    if (clustered && c.car) {
+      // halo: psi of the LOOK tiles below and above this rank's range, drifted here from the neighbouring ranks'
+      // elements (L2 loads: another CTA wrote them) into the cells behind the ring that ell_cl points at.  Nothing of
+      // a tile is overwritten before the cluster barrier below, so in-place leapfrogs are safe.
+      for (int h = 0; h < 2; ++h) {
+        const int t0h = h == 0 ? ta - LOOK : tb;
+        for (int e = tid; e < LOOK * kTile; e += kBlock) {
+          const int tile = t0h + e / kTile;
+          double qn = 0.0;
+          if (tile >= 0 && tile < m.NT && (tile < ta || tile >= tb)) {
+            const int el = m.o_psi + tile * kTile + (e % kTile);
+            qn = __ldcg(sq + el);
+            if (LEAP) qn += eps * __ldcg(minv + el) * (__ldcg(sp + el) - 0.5 * eps * __ldcg(sg + el));
+          }
+          halo[h * LOOK * kTile + e] = qn;
+        }
       }
-      if (write_q) dq[e] = qn;
     }
-    __syncthreads();
+    // small block: half-kick + drift (or copy) in batches of independent loads; the new values are staged in shared
+    // memory for finish_small() (no read-back from HBM) and written to HBM.  Every rank of a cluster stages the small
+    // block for itself; rank 0 alone writes it, in a second pass after the cluster barrier (an in-place leapfrog must
+    // not overwrite what another rank is still reading).
+    auto small_pass = [&](bool to_smem, bool to_hbm) {
+      for (int i0 = tid; i0 < m.nsmall_pad; i0 += kUB * kBlock) {
+        double qv[kUB], pv[kUB], gv[kUB], wv[kUB];
+#pragma unroll
+        for (int u = 0; u < kUB; ++u) {
+          const int e = m.o_small + i0 + u * kBlock;
+          const bool in = i0 + u * kBlock < m.nsmall_pad;
+          qv[u] = in ? sq[e] : 0.0;
+          pv[u] = (LEAP && in) ? sp[e] : 0.0;
+          gv[u] = (LEAP && in) ? sg[e] : 0.0;
+          wv[u] = (LEAP && in) ? minv[e] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kUB; ++u) {
+          const int i = i0 + u * kBlock, e = m.o_small + i;
+          if (i < m.nsmall_pad) {
+            double qn = qv[u];
+            if (LEAP) {
+              const double ph = pv[u] - 0.5 * eps * gv[u];
+              qn += eps * wv[u] * ph;
+              if (to_hbm) dp[e] = ph;
+            }
+            if (to_hbm && write_q) dq[e] = qn;
+            if (to_smem) {
+              if (i < m.nbeta) Bs()[i] = qn;
+              else if (i < m.nsmall) Ss()[i - m.nbeta] = qn;
+            }
+          }
+        }
+      }
+    };
     Scalars sc;
-    load_small(dq, sc);
-    for (int idx = tid; idx < m.nbeta; idx += kBlock) adjB[idx] = 0.0;
+    small_pass(true, !clustered);
+    __syncthreads();
+    finish_small(sc);
+    if (clustered) {
+      cluster_sync();   // every halo and every rank's copy of the small block is read: in-place writes may begin
+      if (crank == 0) small_pass(false, true);
+    }
+    for (int idx = tid; idx < m.nbeta; idx += kBlock) As()[idx] = 0.0;
     const double tails = sc.log1m_theta;
     const double sig03 = 0.3 * sc.sigma;
     const double theta = sc.theta, om_theta = 1.0 - sc.theta, tau = sc.tau, a_car = sc.a;
@@ -778,7 +961,10 @@ struct DevOps {
     // the non-compositional kernels have registers to spare and few tiles per evaluation: they fold the
     // eigenvalue term into the tile loop; the compositional ones (register-critical loop) leave it to finish()
     constexpr bool kEigInLoop = KT <= 2;
-    const int n_eigg = kEigInLoop ? m.n_eigg : 0;
+    // (a cluster splits the eigenvalue groups evenly over its ranks)
+    const int eig_per = (m.n_eigg + csize - 1) / csize;
+    const int eig0 = kEigInLoop ? crank * eig_per : 0;
+    const int n_eigg = kEigInLoop ? min(m.n_eigg, eig0 + eig_per) : 0;
     const double *eigg = m.eigg, *eiggm = m.eiggm;
 
     if (c.car)
@@ -793,7 +979,7 @@ struct DevOps {
       // the barrier so that their latency overlaps the drift of the next tile and the barrier wait
       double e[KP];
       if (KT > 1) {
-        const double *Ej = c.E + ((size_t)k * KT) * kTile + tid;
+        const double *Ej = c.E + ((size_t)(c.ta + k) * KT) * kTile + tid;
 #pragma unroll
         for (int i = 0; i < KP; ++i) e[i] = (i < KT) ? __ldg(Ej + (size_t)i * kTile) : 0.0;
       } else {
@@ -802,7 +988,7 @@ struct DevOps {
       if (kEigInLoop && c.car) {
         // one group of eight distinct eigenvalues of the CAR precision per thread and tile (the groups fill the
         // first tiles densely: whole warps either have one or skip the block)
-        const int ei = k * kTile + tid;
+        const int ei = eig0 + k * kTile + tid;
         if (ei < n_eigg) eig_group_terms(eigg + (size_t)ei * kEigGroup, __ldg(eiggm + ei), a_car, a_ldet, a_dldet);
       }
       PW(w_psi, if (c.car && k + LOOK < NT) drift_tile<LEAP, LOOK>(c, k + LOOK, eps));
@@ -818,7 +1004,7 @@ struct DevOps {
       const double *rd = smem_d + c.rest_o + (seq & 1u) * (c.stage_bytes >> 3);
       const int *ri = reinterpret_cast<const int *>(rd + 5 * kTile);
       const double *ringp = smem_d + c.ring_o;
-      const int j = k * kTile + tid;
+      const int j = (c.ta + k) * kTile + tid;
       const int kraw = ri[kTile + tid];  // -1 in the padding
       const int bin = kraw < 0 ? -1 : (kraw & 0xFFFFFF);
       double gj = 0.0;
@@ -834,6 +1020,16 @@ struct DevOps {
         double ll;
         if (KT == 1) {
           ll = bj[0];
+        } else if (KT % 2 == 0) {
+          // two accumulation chains, the beta row in 16-byte loads (its offset is even whenever KT is)
+          double l0 = 0.0, l1 = 0.0;
+#pragma unroll
+          for (int i = 0; i < KT; i += 2) {
+            const double2 b2 = *reinterpret_cast<const double2 *>(bj + i);
+            l0 += b2.x * e[i];
+            l1 += b2.y * e[i + 1];
+          }
+          ll = l0 + l1;
         } else {
           ll = 0.0;
 #pragma unroll
@@ -958,8 +1154,50 @@ struct DevOps {
     const long long t_fin = clock64();
     if (c.zi) a_lp += zi_prod.log_value();
     // the zi-only part of d/dtheta was accumulated as (1 - e^{-mu}) / s; finish() expects it in a_dth
-    finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out, sp, rho_out,
-                 a_pp, pp_out, kEigInLoop, a_ldet, a_dldet);
+    if (!clustered) {
+      finish<LEAP>(sc, a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, tails, dq, dg, dp, eps, V_out, K_out, finite_out, sp, rho_out,
+                   a_pp, pp_out, kEigInLoop, a_ldet, a_dldet);
+    } else {
+      // cluster: every rank publishes its partial sums (and holds its partial beta-gradient bins in adjB); rank 0
+      // adds them up in rank order, runs the epilogue of the small block alone and broadcasts the four results
+      double r[kRedMax] = {a_lp, a_ng, a_qD, a_qW, a_dth, a_kin, a_g2, a_pp, a_ldet, a_dldet, 0.0, 0.0};
+      block_sum<kRedMax>(r, Rs());
+      if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kRedMax; ++i) cl_part[i] = r[i];
+      }
+      cluster_sync();
+      if (crank == 0) {
+        double t[kRedMax];
+#pragma unroll
+        for (int i = 0; i < kRedMax; ++i) t[i] = 0.0;
+        for (int rk = 0; rk < csize; ++rk) {
+          const double *rp = remote(cl_part, rk);
+#pragma unroll
+          for (int i = 0; i < kRedMax; ++i) t[i] += rp[i];
+        }
+        const int b0i = (m.bot0 * m.C) * KT, b1i = m.nbeta;
+        for (int rk = 1; rk < csize; ++rk) {
+          const double *ra = remote(As(), rk);
+          for (int idx = b0i + tid; idx < b1i; idx += kBlock) As()[idx] += ra[idx];
+        }
+        __syncthreads();
+        const bool lead = tid == 0;   // the totals enter finish()'s own block reduction once
+        double Vv = 0.0, Kv = 0.0, ppv = 0.0;
+        bool fin = true;
+        finish<LEAP>(sc, lead ? t[0] : 0.0, lead ? t[1] : 0.0, lead ? t[2] : 0.0, lead ? t[3] : 0.0, lead ? t[4] : 0.0,
+                     lead ? t[5] : 0.0, lead ? t[6] : 0.0, tails, dq, dg, dp, eps, &Vv, &Kv, &fin, sp, rho_out,
+                     lead ? t[7] : 0.0, &ppv, kEigInLoop, lead ? t[8] : 0.0, lead ? t[9] : 0.0);
+        // (finish() has left V, K, finite, pp in cl_bcast for the other ranks)
+        (void)Vv; (void)Kv; (void)fin; (void)ppv;
+      }
+      cluster_sync();
+      const double *rb = remote(cl_bcast, 0);
+      if (V_out) *V_out = rb[0];
+      if (K_out) *K_out = rb[1];
+      if (finite_out) *finite_out = rb[2] != 0.0;
+      if (pp_out) *pp_out = rb[3];
+    }
     cyc_pro += t_loop - t_begin;
     cyc_fin += clock64() - t_fin;
   }
@@ -973,8 +1211,8 @@ struct DevOps {
   __device__ void eval(const double *sq, const double *sg, const double *sp, double *dq, double *dg,
                        double *dp, double eps, double *V_out, double *K_out, bool *finite_out,
                        double *rho_out = nullptr, double *pp_out = nullptr) {
-    // neighbours up to two tiles away (317-wide Visium-HD rows) only for the non-compositional kernels
-    if (m.tiled && KT <= 2 && m.look == 2) eval_tiled<LEAP, (KT <= 2 ? 2 : 1)>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
+    // neighbours up to two tiles away: 257- to 512-wide rows (Visium-HD bins), compositional kernels included
+    if (m.tiled && m.look == 2) eval_tiled<LEAP, 2>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
     else if (m.tiled) eval_tiled<LEAP, 1>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
     else eval_generic<LEAP>(sq, sg, sp, dq, dg, dp, eps, V_out, K_out, finite_out, rho_out, pp_out);
   }
@@ -1011,7 +1249,7 @@ struct DevOps {
 
     Scalars sc;
     load_small(dq, sc);
-    for (int idx = tid; idx < m.nbeta; idx += kBlock) adjB[idx] = 0.0;
+    for (int idx = tid; idx < m.nbeta; idx += kBlock) As()[idx] = 0.0;
     __syncthreads();
 
     const double heads = sc.log_theta;
@@ -1041,7 +1279,7 @@ struct DevOps {
         kj = m.key[j] & 0xFFFFFF;
         const double eps_j = noi[j];
         double ll;
-        const double *bj = B + (m.bot0 * m.C) * m.K + kj * m.K;
+        const double *bj = Bs() + (m.bot0 * m.C) * m.K + kj * m.K;
         if (KT == 1) {
           ll = bj[0];
           e[0] = 1.0;
@@ -1174,18 +1412,19 @@ struct DevOps {
     const long long t0 = clock64();
     double *p = vec(pv);
     double k = 0.0;
-    for (int e = threadIdx.x; e < m.Di; e += kBlock) {
-      const int si = m.imap[e];
-      double v = 0.0;
-      if (si >= 0) {
-        const double mi = minv[e];
-        v = rng_normal(key, purpose, sub, iter, (uint32_t)si) / sqrt(mi);
-        k += mi * v * v;
+    for (int sgi = 0; sgi < nseg; ++sgi)
+      for (int e = seg_lo[sgi] + threadIdx.x; e < seg_hi[sgi]; e += kBlock) {
+        const int si = m.imap[e];
+        double v = 0.0;
+        if (si >= 0) {
+          const double mi = minv[e];
+          v = rng_normal(key, purpose, sub, iter, (uint32_t)si) / sqrt(mi);
+          k += mi * v * v;
+        }
+        p[e] = v;
       }
-      p[e] = v;
-    }
     double r[1] = {k};
-    block_sum<1>(r, red);
+    chain_sum<1>(r);
     sample_is_q0 = true;
     cyc_other += clock64() - t0;
     return 0.5 * r[0];
@@ -1217,10 +1456,9 @@ struct DevOps {
     const double *Cpb = vec(C.pb), *Cpe = vec(C.pe), *Crho = vec(C.rho);
     double *out = vec(rho_out);
     double a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0;
-    const int Di = m.Di;
     const double *mv = minv;
-    // streaming pass over 7 vectors: two strips of 16 B per thread in flight (14 independent loads) keep a
-    // lone merging CTA from being latency bound while its neighbours on the SM do arithmetic
+    // streaming pass over 7 vectors: three strips of 16 B per thread in flight (21 independent loads): a merging CTA
+    // runs next to CTAs doing arithmetic, so its own bytes in flight set its speed (two strips: 22 GB/s per CTA at c3)
     auto body = [&](const double2 w, const double2 lpb, const double2 lpe, const double2 lrh, const double2 cpb,
                     const double2 cpe, const double2 crh, double *o) {
       double2 rs;
@@ -1237,38 +1475,44 @@ struct DevOps {
       *reinterpret_cast<double2 *>(o) = rs;
     };
 #define CSP_LD2(p, e) (*reinterpret_cast<const double2 *>((p) + (e)))
-    int e = 2 * threadIdx.x;
-    for (; e + 2 * kBlock < Di; e += 4 * kBlock) {
-      const int f = e + 2 * kBlock;
-      const double2 w0 = CSP_LD2(mv, e), w1 = CSP_LD2(mv, f);
-      const double2 p0 = CSP_LD2(Lpb, e), p1 = CSP_LD2(Lpb, f);
-      const double2 q0 = CSP_LD2(Lpe, e), q1 = CSP_LD2(Lpe, f);
-      const double2 r0 = CSP_LD2(Lrho, e), r1 = CSP_LD2(Lrho, f);
-      const double2 s0 = CSP_LD2(Cpb, e), s1 = CSP_LD2(Cpb, f);
-      const double2 t0 = CSP_LD2(Cpe, e), t1 = CSP_LD2(Cpe, f);
-      const double2 u0 = CSP_LD2(Crho, e), u1 = CSP_LD2(Crho, f);
-      body(w0, p0, q0, r0, s0, t0, u0, out + e);
-      body(w1, p1, q1, r1, s1, t1, u1, out + f);
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+      const int hi = seg_hi[sgi];
+      int e = seg_lo[sgi] + 2 * threadIdx.x;
+      for (; e + 4 * kBlock < hi; e += 6 * kBlock) {   // three strips: 21 independent 16-byte loads per thread
+        const int f = e + 2 * kBlock, h = e + 4 * kBlock;
+        const double2 w0 = CSP_LD2(mv, e), w1 = CSP_LD2(mv, f), w2 = CSP_LD2(mv, h);
+        const double2 p0 = CSP_LD2(Lpb, e), p1 = CSP_LD2(Lpb, f), p2 = CSP_LD2(Lpb, h);
+        const double2 q0 = CSP_LD2(Lpe, e), q1 = CSP_LD2(Lpe, f), q2 = CSP_LD2(Lpe, h);
+        const double2 r0 = CSP_LD2(Lrho, e), r1 = CSP_LD2(Lrho, f), r2 = CSP_LD2(Lrho, h);
+        const double2 s0 = CSP_LD2(Cpb, e), s1 = CSP_LD2(Cpb, f), s2 = CSP_LD2(Cpb, h);
+        const double2 t0 = CSP_LD2(Cpe, e), t1 = CSP_LD2(Cpe, f), t2 = CSP_LD2(Cpe, h);
+        const double2 u0 = CSP_LD2(Crho, e), u1 = CSP_LD2(Crho, f), u2 = CSP_LD2(Crho, h);
+        body(w0, p0, q0, r0, s0, t0, u0, out + e);
+        body(w1, p1, q1, r1, s1, t1, u1, out + f);
+        body(w2, p2, q2, r2, s2, t2, u2, out + h);
+      }
+      for (; e < hi; e += 2 * kBlock)
+        body(CSP_LD2(mv, e), CSP_LD2(Lpb, e), CSP_LD2(Lpe, e), CSP_LD2(Lrho, e), CSP_LD2(Cpb, e), CSP_LD2(Cpe, e),
+             CSP_LD2(Crho, e), out + e);
     }
-    for (; e < Di; e += 2 * kBlock)
-      body(CSP_LD2(mv, e), CSP_LD2(Lpb, e), CSP_LD2(Lpe, e), CSP_LD2(Lrho, e), CSP_LD2(Cpb, e), CSP_LD2(Cpe, e),
-           CSP_LD2(Crho, e), out + e);
     double r[6] = {a1, a2, b1, b2, c1, c2};
-    block_sum<6>(r, red);
+    chain_sum<6>(r);
     return (r[1] > 0 && r[0] > 0) && (r[3] > 0 && r[2] > 0) && (r[5] > 0 && r[4] > 0);
   }
   __device__ __noinline__ void copy_vec(double *dst, const double *src) {
-    const int Di = m.Di;
-    int e = 2 * threadIdx.x;
-    for (; e + 6 * kBlock < Di; e += 8 * kBlock) {  // four 16-byte loads in flight per thread
-      const double2 a = CSP_LD2(src, e), b = CSP_LD2(src, e + 2 * kBlock), c = CSP_LD2(src, e + 4 * kBlock),
-                    d = CSP_LD2(src, e + 6 * kBlock);
-      *reinterpret_cast<double2 *>(dst + e) = a;
-      *reinterpret_cast<double2 *>(dst + e + 2 * kBlock) = b;
-      *reinterpret_cast<double2 *>(dst + e + 4 * kBlock) = c;
-      *reinterpret_cast<double2 *>(dst + e + 6 * kBlock) = d;
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+      const int hi = seg_hi[sgi];
+      int e = seg_lo[sgi] + 2 * threadIdx.x;
+      for (; e + 6 * kBlock < hi; e += 8 * kBlock) {  // four 16-byte loads in flight per thread
+        const double2 a = CSP_LD2(src, e), b = CSP_LD2(src, e + 2 * kBlock), c = CSP_LD2(src, e + 4 * kBlock),
+                      d = CSP_LD2(src, e + 6 * kBlock);
+        *reinterpret_cast<double2 *>(dst + e) = a;
+        *reinterpret_cast<double2 *>(dst + e + 2 * kBlock) = b;
+        *reinterpret_cast<double2 *>(dst + e + 4 * kBlock) = c;
+        *reinterpret_cast<double2 *>(dst + e + 6 * kBlock) = d;
+      }
+      for (; e < hi; e += 2 * kBlock) *reinterpret_cast<double2 *>(dst + e) = CSP_LD2(src, e);
     }
-    for (; e < Di; e += 2 * kBlock) *reinterpret_cast<double2 *>(dst + e) = CSP_LD2(src, e);
     __syncthreads();
   }
   __device__ void copy_q_to_prop(int z) {
@@ -1289,46 +1533,55 @@ struct DevOps {
     cyc_copy += clock64() - t0;
   }
   __device__ __noinline__ void init_uniform(uint32_t attempt, double radius) {
-    for (int e = threadIdx.x; e < m.Di; e += kBlock) {
-      const int si = m.imap[e];
-      q_cur[e] = si >= 0 ? rng_init(key, attempt, (uint32_t)si, radius) : 0.0;
-    }
+    for (int sgi = 0; sgi < nseg; ++sgi)
+      for (int e = seg_lo[sgi] + threadIdx.x; e < seg_hi[sgi]; e += kBlock) {
+        const int si = m.imap[e];
+        q_cur[e] = si >= 0 ? rng_init(key, attempt, (uint32_t)si, radius) : 0.0;
+      }
     __syncthreads();
   }
   __device__ __noinline__ void set_unit_metric() {
-    for (int e = threadIdx.x; e < m.Di; e += kBlock) { minv[e] = 1.0; wm[e] = 0.0; wm2[e] = 0.0; }
+    for (int sgi = 0; sgi < nseg; ++sgi)
+      for (int e = seg_lo[sgi] + threadIdx.x; e < seg_hi[sgi]; e += kBlock) { minv[e] = 1.0; wm[e] = 0.0; wm2[e] = 0.0; }
     __syncthreads();
   }
   __device__ __noinline__ void welford_add(double n) {
-    for (int e = threadIdx.x; e < m.Di; e += kBlock) {
-      const double q = q_cur[e];
-      const double delta = q - wm[e];
-      const double mean = wm[e] + delta / n;
-      wm[e] = mean;
-      wm2[e] += (q - mean) * delta;
-    }
+    for (int sgi = 0; sgi < nseg; ++sgi)
+      for (int e = seg_lo[sgi] + threadIdx.x; e < seg_hi[sgi]; e += kBlock) {
+        const double q = q_cur[e];
+        const double delta = q - wm[e];
+        const double mean = wm[e] + delta / n;
+        wm[e] = mean;
+        wm2[e] += (q - mean) * delta;
+      }
     __syncthreads();
   }
   __device__ __noinline__ void metric_update(double n) {
-    for (int e = threadIdx.x; e < m.Di; e += kBlock) {
-      double v = minv[e];
-      if (n > 1) v = wm2[e] / (n - 1.0);
-      minv[e] = (m.imap[e] >= 0) ? (n / (n + 5.0)) * v + 1e-3 * (5.0 / (n + 5.0)) : 1.0;
-      wm[e] = 0.0;
-      wm2[e] = 0.0;
-    }
+    for (int sgi = 0; sgi < nseg; ++sgi)
+      for (int e = seg_lo[sgi] + threadIdx.x; e < seg_hi[sgi]; e += kBlock) {
+        double v = minv[e];
+        if (n > 1) v = wm2[e] / (n - 1.0);
+        minv[e] = (m.imap[e] >= 0) ? (n / (n + 5.0)) * v + 1e-3 * (5.0 / (n + 5.0)) : 1.0;
+        wm[e] = 0.0;
+        wm2[e] = 0.0;
+      }
     __syncthreads();
   }
   // one sampling draw: sampler columns, the small block, optional full theta, and the streaming
   // summaries summarize_stan_hdf5 needs (/root/reference/splotch/utils.py:234-257)
   __device__ __noinline__ void record_draw(const DrawInfo &info, int s) {
     const int tid = threadIdx.x;
-    if (out_diag && tid == 0) {
+    const bool clustered = CL && csize > 1;
+    // cluster: the ranks have just committed their parts of q_cur; rank 0 reads all of it (through L2) for the spot
+    // summaries, every rank writes its own elements of the draw
+    if (clustered) cluster_sync();
+    const bool lead = !clustered || crank == 0;
+    if (out_diag && tid == 0 && lead) {
       double *r = out_diag + (size_t)s * 7;
       r[0] = info.lp; r[1] = info.accept_stat; r[2] = info.stepsize; r[3] = info.treedepth;
       r[4] = info.n_leapfrog; r[5] = info.divergent; r[6] = info.energy;
     }
-    if (out_small)
+    if (out_small && lead)
       for (int i = tid; i < m.nsmall; i += kBlock) {
         int o;
         if (i < m.nbeta) {
@@ -1340,11 +1593,12 @@ struct DevOps {
         if (o >= 0) out_small[(size_t)s * m.nsmall_true + o] = q_cur[m.o_small + i];
       }
     if (out_theta)
-      for (int e = tid; e < m.Di; e += kBlock) {
-        const int si = m.imap[e];
-        if (si >= 0) out_theta[(size_t)s * m.D + si] = q_cur[e];
-      }
-    if (out_summ) {
+      for (int sgi = 0; sgi < nseg; ++sgi)
+        for (int e = seg_lo[sgi] + tid; e < seg_hi[sgi]; e += kBlock) {
+          const int si = m.imap[e];
+          if (si >= 0) out_theta[(size_t)s * m.D + si] = q_cur[e];
+        }
+    if (out_summ && lead) {
       Scalars sc;
       load_small(q_cur, sc);
       const double n = (double)(s + 1);
@@ -1353,7 +1607,7 @@ struct DevOps {
              *vla = out_summ + 3 * (size_t)m.N, *mps = out_summ + 4 * (size_t)m.N,
              *vps = out_summ + 5 * (size_t)m.N;
       for (int j = tid; j < m.N; j += kBlock) {
-        const double *bj = B + (m.bot0 * m.C) * m.K + (m.key[j] & 0xFFFFFF) * m.K;
+        const double *bj = Bs() + (m.bot0 * m.C) * m.K + (m.key[j] & 0xFFFFFF) * m.K;
         double ll;
         if (KT == 1) {
           ll = bj[0];
@@ -1363,8 +1617,8 @@ struct DevOps {
           for (int k = 0; k < m.K; ++k) ll += bj[k] * Ej[(size_t)k * kTile];
         }
         double psi_j = 0.0;
-        if (m.car) { psi_j = q_cur[m.o_psi + j]; ll += psi_j; }
-        ll += sig03 * q_cur[m.o_noise + j];
+        if (m.car) { psi_j = clustered ? __ldcg(q_cur + m.o_psi + j) : q_cur[m.o_psi + j]; ll += psi_j; }
+        ll += sig03 * (clustered ? __ldcg(q_cur + m.o_noise + j) : q_cur[m.o_noise + j]);
         double d = ll - mll[j], mean = mll[j] + d / n;
         mll[j] = mean; vll[j] += (ll - mean) * d;
         const double la = exp(ll);

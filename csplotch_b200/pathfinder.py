@@ -63,10 +63,13 @@ class PathfinderResult:
 
 
 # ------------------------------------------------------------------------------------------------ variates
-def _normals(seed: int, purpose: int, path: int, block: int, shape):
-    """Standard normals keyed by (seed, purpose, path, block); the same for every gene."""
+def _normals(seed: int, purpose: int, path: int, block: int, shape, gene_id: int = 0):
+    """Standard normals keyed by (seed, purpose, path, block, gene id).  The draws a gene returns (purpose 2) carry its
+    id, so genes and paths get independent streams whatever the batch; the ELBO estimates (purpose 1) use common random
+    numbers across genes on purpose (gene_id 0: one (num_elbo_draws, D) matrix per L-BFGS iteration instead of one
+    per gene-path — each gene's estimate is unbiased either way, and the host generates 10^3 times fewer variates)."""
     key = (int(seed) & 0xFFFFFFFF) | (int(purpose) << 32) | (int(path) << 40)
-    bg = np.random.Philox(key=key, counter=[int(block), 0, 0, 0])
+    bg = np.random.Philox(key=key, counter=[int(block), int(gene_id), 0, 0])
     return np.random.Generator(bg).standard_normal(shape)
 
 
@@ -486,7 +489,7 @@ def pathfinder(target, *, num_paths: int = 4, num_draws: int = 1000, num_out: in
             part = best.take(np.array([r]))
             for b0 in range(0, num_draws, blk):
                 nb = min(blk, num_draws - b0)
-                u = _normals(seed, 2, int(path_of[r]), b0 // blk, (blk, D))[:nb]
+                u = _normals(seed, 2, int(path_of[r]), b0 // blk, (blk, D), target.gene_id0 + gi)[:nb]
                 phi, logq = part.draw(u)
                 lps.append(lp_only(phi[0], np.full(nb, gi, dtype=np.int32)))
                 lpas.append(logq[0])
@@ -508,7 +511,7 @@ def pathfinder(target, *, num_paths: int = 4, num_draws: int = 1000, num_out: in
             part = best.take(np.array([r]))
             didx = where[pick[sel], 1]
             for b in np.unique(didx // blk):
-                u = _normals(seed, 2, int(path_of[r]), int(b), (blk, D))
+                u = _normals(seed, 2, int(path_of[r]), int(b), (blk, D), target.gene_id0 + gi)
                 inb = didx // blk == b
                 phi, _ = part.draw(u[didx[inb] % blk])
                 out_draws[gi, sel[inb]] = phi[0]

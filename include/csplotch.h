@@ -195,6 +195,10 @@ int32_t csplotch_sampler_counters(csplotch_sampler *s, int64_t *n_leapfrog, int6
  * candidate copies, everything else}, the number of merge passes and candidate copies, then the cycles of
  * the log-density pass spent before its tile loop (prologue) and after it (reductions, small block) */
 int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out8);
+/* how the sampler's launches are laid out: gene-chains resident at once, and the CTAs of the thread-block cluster that
+ * works on each (1 for short designs or thousands of chains; 2 or 4 when few chains of a long design would otherwise
+ * leave the launch waiting for its deepest tree; CSPLOTCH_CLUSTER=1|2|4 at csplotch_model_create forces a size) */
+int32_t csplotch_sampler_layout(csplotch_sampler *s, int32_t *resident_chains, int32_t *cluster_size);
 /* diagnostic: nanoseconds every resident CTA of the last launch was busy (ns[n_slots]; pass ns = NULL to query n_slots):
  * max - mean is the tail of the launch that the longest-first queue order is there to shorten */
 int32_t csplotch_sampler_slot_ns(csplotch_sampler *s, int64_t *ns, int32_t cap, int32_t *n_slots);
@@ -211,6 +215,9 @@ int32_t csplotch_sampler_status(csplotch_sampler *s, int32_t *status, int32_t *i
 int32_t csplotch_sampler_get_draws(csplotch_sampler *s, double *diag, double *small, int32_t *n_draws);
 /* full unconstrained draws [G][num_chains][num_samples][dim] (needs cfg.keep_draws) */
 int32_t csplotch_sampler_get_theta_draws(csplotch_sampler *s, double *theta);
+/* the same for genes g0 .. g0 + n_genes - 1 of the batch only: theta [n_genes][num_chains][num_samples][dim] (the CSV
+ * writer walks over the batch a few genes at a time; all draws of a c3-sized batch exceed host memory) */
+int32_t csplotch_sampler_get_theta_draws_range(csplotch_sampler *s, int32_t g0, int32_t n_genes, double *theta);
 /* current position, adapted step size and inverse metric: [G][num_chains][dim], [G][num_chains] */
 int32_t csplotch_sampler_get_state(csplotch_sampler *s, double *theta, double *stepsize, double *inv_metric);
 /* posterior summaries pooled over chains, the layout summarize_stan_hdf5 writes
@@ -219,6 +226,22 @@ int32_t csplotch_sampler_get_state(csplotch_sampler *s, double *theta, double *s
 int32_t csplotch_sampler_get_spot_summaries(csplotch_sampler *s, double *log_lambda_mean,
                                             double *log_lambda_std, double *lambda_mean, double *lambda_std,
                                             double *psi_mean, double *psi_std);
+
+/* ---- CAR pre-compute on the GPU ---------------------------------------------------
+ * Stands in for the CAR part of generate_dictionary (/root/reference/splotch/utils.py:735-765): per tissue the
+ * eigenvalues of D^-1/2 W D^-1/2 (utils.py:749-755), for tissues with more than `exact_max_n` spots (reference: >= 10 000)
+ * the chunked approximation eigs_square_chunking (utils.py:629-670: coordinate squares of rint(sqrt(chunk_spots)) units,
+ * degrees inside the chunk), all eigenvalues concatenated and sorted (utils.py:759); D_sparse = degrees (utils.py:739);
+ * U, V = 1-based CSR of the symmetric adjacency (sparse_to_csr_indptr, utils.py:592-614).  Identical tissues / chunks
+ * are solved once (n_solves = dense eigenproblems actually solved).  Dense matrices are assembled on the device and
+ * solved by cuSOLVER (loaded on first use).
+ * N_spots[N_tissues]; W_sparse[W_n][2] 1-based global spot ids, every pair once, both ends in one tissue;
+ * coords[N][2] non-negative integer x, y (only read for tissues beyond exact_max_n; may be NULL otherwise);
+ * chunk_spots <= 0: 10 000; exact_max_n <= 0: 9 999 (the reference's rule), at most 40 000.
+ * Outputs (any may be NULL): eig_values[N] ascending, U[N+1], V[2 W_n], D_sparse[N]. */
+int32_t csplotch_car_precompute(int32_t N_tissues, const int32_t *N_spots, int32_t W_n, const int32_t *W_sparse,
+                                const int32_t *coords, int32_t chunk_spots, int32_t exact_max_n, double *eig_values,
+                                int32_t *U, int32_t *V, double *D_sparse, int32_t *n_solves);
 
 /* ---- ingestion fast path ------------------------------------------------------
  * Stands in for read_rdump (/root/reference/splotch/utils.py:78-111) on the per-gene part of the

@@ -4,7 +4,7 @@ scripts/ncu_capture.sh <tag> k_nuts_advance scripts/profile_nuts.py <shape> <G> 
 import csv, json, sys
 
 tag, shape = sys.argv[1], sys.argv[2]
-idx = int(sys.argv[3]) if len(sys.argv) > 3 else 1        # ncu_capture.sh skips one matching launch
+idx = int(sys.argv[3]) if len(sys.argv) > 3 else 1        # index into the launches list of the launch ncu profiled (NCU_SKIP)
 rows = list(csv.reader(open("gpurun_out/raw_%s.csv" % tag)))
 hdr, unit, val = rows[0], rows[1], rows[2]
 

@@ -452,3 +452,63 @@ def test_lp_grad_matches_committed_known_answers(golden_dir):
     lp0 = batch.log_prob_grad(theta, gene_of=gene_of, jacobian=False, want_grad=False)
     want0 = z["lp_no_jacobian"].reshape(21)
     assert np.max(np.abs(lp0 - want0) / np.maximum(1.0, np.abs(want0))) < 1e-10
+
+
+def test_torch_tensor_front_end_is_zero_copy_and_equal():
+    """csplotch_b200.torch_api: CUDA tensors handed to the `_dev` entry points by pointer give the numbers of the
+    host-buffer calls (north star: a thin PyTorch layer over the C ABI)."""
+    import torch
+    from csplotch_b200 import torch_api
+    family = "comp_splotch_stan_model"
+    shared, genes = _tiny(family, 3, 1, 1, seed=21, G=3)
+    model = api.Model(shared, family)
+    host = api.Batch(model, genes["counts"], genes["beta_prior_mean"], genes["beta_prior_std"], gene_id0=4)
+    dev = torch_api.batch_from_tensor(model, torch.as_tensor(genes["counts"], dtype=torch.int32, device="cuda"),
+                                      genes["beta_prior_mean"], genes["beta_prior_std"], gene_id0=4)
+    rng = np.random.default_rng(1)
+    theta = rng.normal(0, 1, (6, model.dim))
+    gene_of = np.arange(6, dtype=np.int32) % 3
+    lp0, g0 = host.log_prob_grad(theta, gene_of=gene_of)
+    lp1, g1 = torch_api.log_prob_grad(dev, torch.as_tensor(theta, device="cuda"), torch.as_tensor(gene_of, device="cuda"))
+    assert lp1.is_cuda and g1.is_cuda
+    assert np.array_equal(lp1.cpu().numpy(), lp0) and np.array_equal(g1.cpu().numpy(), g0)
+    # and the device batch samples like the host one
+    cfg = api.nuts_cfg(8, 3, 2, seed=2)
+    a = api.Sampler(host, cfg).run().draws()
+    b = api.Sampler(dev, cfg).run().draws()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_compositional_wide_rows_use_the_tiled_path():
+    """a compositional Visium-HD design (K = 10, 317-wide rows: neighbours two 256-spot tiles away)
+    runs on the staged pipeline with LOOK = 2 instead of dropping to the generic kernel; parity as everywhere."""
+    family = "comp_splotch_stan_model"
+    rng = np.random.default_rng(12)
+    h, w, K, C = 5, 317, 10, 3
+    p = synth.grid4_pairs(h, w)
+    n = h * w
+    E = synth.scale_and_round(rng.dirichlet(np.full(K, 0.5), size=2 * n))
+    shared = synth.build_shared([n, n], [p, p], [synth.car_eigenvalues(p, n)] * 2, rng.integers(1, C + 1, size=2 * n), [1, 2],
+                                (1, 2), [1, 1], [], np.clip(rng.lognormal(0, 0.5, 2 * n), 0.05, 8), C, zi=1, car=1, E=E)
+    genes = synth.simulate_counts(shared, 2, 13)
+    b = _batch(shared, genes, family, gene_id0=2)
+    theta = rng.normal(0, 0.8, (2, b.model.dim))
+    lp, grad = b.log_prob_grad(theta, gene_of=[0, 1])
+    for i in range(2):
+        o = oracle.Oracle(synth.gene_dict(shared, genes, i), family)
+        lp0, g0 = o.log_prob_grad(theta[i])
+        assert abs(lp[i] - lp0) < 1e-10 * abs(lp0) and _rel(grad[i], g0) < 1e-10
+        p0 = rng.normal(0, 1, b.model.dim)
+        th, pp, H = b.leapfrog_fixed(theta[i] * 0.3, p0, np.ones(b.model.dim), 1e-3, 12, gene_of=[i])
+        th0, pp0, H0 = o.leapfrog_fixed(theta[i] * 0.3, p0, np.ones(b.model.dim), 1e-3, 12)
+        assert _rel(th[0], th0) < 1e-8 and _rel(pp[0], pp0) < 1e-8 and abs(H[0] - H0) < 1e-8 * abs(H0)
+    # the staged pipeline is several times faster than the generic kernel: same design forced onto the fallback
+    ms_tiled = b.leapfrog_bench(64, 1e-4, 4, 2)
+    import os
+    os.environ["CSPLOTCH_FORCE_ORDER"] = "generic"
+    try:
+        bg = _batch(shared, genes, family, gene_id0=2)
+        ms_generic = bg.leapfrog_bench(64, 1e-4, 4, 2)
+    finally:
+        del os.environ["CSPLOTCH_FORCE_ORDER"]
+    assert ms_tiled < ms_generic

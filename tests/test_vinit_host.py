@@ -105,8 +105,8 @@ class _Sampler:
         idx += [i for n, i, t in api.param_layout(m) if t != "id"]
         return self._diag, self._theta[..., idx], np.full((self.G, self.nch), self.cfg.num_samples, dtype=np.int32)
 
-    def theta_draws(self):
-        return self._theta
+    def theta_draws(self, g0=0, n_genes=None):
+        return self._theta[g0:(None if n_genes is None else g0 + n_genes)]
 
     def counters(self):
         return dict(n_leapfrog=int(self._diag[..., 4].sum()), n_grad=int(self._diag[..., 4].sum()), n_divergent=0,
