@@ -219,11 +219,22 @@ def cpu_reference_run(family, shared, genes, iters, n_threads, n_chains=4):
         G, n_chains, iters, n_threads)
 
 
-def cpu_iters_for(family, shared, genes, n_threads, target_s):
-    """Pick the number of transitions so that one bounded CPU sample takes about target_s seconds."""
-    g, dt, _ = cpu_reference_run(family, shared, genes, 2, n_threads)
-    per_iter = max(dt / 2.0, 1e-4)
-    return int(min(400, max(2, target_s / per_iter)))
+def cpu_sample(family, shared, genes, n_threads, target_s):
+    """One bounded CPU sample of about target_s seconds: the first `it` transitions from initialisation, `it` grown
+    while the PREDICTED time of the next, longer run stays inside the budget (trees deepen during early warm-up: a
+    max-depth transition of a c3 chain is ~30 s of one host core, so a prediction from the first two transitions alone
+    under-estimates by 10x).  Returns the last run: (grads, seconds, description, iters)."""
+    it = 2
+    g, dt, sample = cpu_reference_run(family, shared, genes, it, n_threads)
+    spent = dt
+    while it < 400:
+        nxt = min(400, max(it + 1, int(it * 1.5)))
+        if 2.0 * dt * nxt / it > target_s - spent:      # (2x: the later transitions are the deeper ones)
+            break
+        it = nxt
+        g, dt, sample = cpu_reference_run(family, shared, genes, it, n_threads)
+        spent += dt
+    return g, dt, sample, it
 
 
 def run_reference(args):
@@ -237,7 +248,8 @@ def run_reference(args):
     # the same genes as the cpu_baseline leg of the GPU arm: the head of the workload's gene list
     family, shared, genes = make_inputs(wl_name, WORKLOADS[wl_name][1], 0, head_only=True)
     nthr = os.cpu_count() or 1
-    iters = args.cpu_iters or cpu_iters_for(family, shared, genes, nthr, 120.0 / max(1, args.steps + args.warmup))
+    # every step is one bounded sample; the whole arm (warm-up + steps) aims at <= ~3 minutes of host time
+    iters = args.cpu_iters or cpu_sample(family, shared, genes, nthr, 150.0 / max(1, args.steps + args.warmup))[3]
     for _ in range(args.warmup):
         cpu_reference_run(family, shared, genes, iters, nthr)
     tot_g, tot_t, sample = 0, 0.0, ""
@@ -530,9 +542,10 @@ def main():
             line["secondary"] = secondary
         if world == 1 and not args.no_cpu:
             nthr = os.cpu_count() or 1
-            family_h, shared_h, genes_h = family, shared, genes
-            cg, cdt, sample = cpu_reference_run(family_h, shared_h, genes_h,
-                                                args.cpu_iters or cpu_iters_for(family_h, shared_h, genes_h, nthr, 15.0), nthr)
+            if args.cpu_iters:
+                cg, cdt, sample = cpu_reference_run(family, shared, genes, args.cpu_iters, nthr)
+            else:
+                cg, cdt, sample, _ = cpu_sample(family, shared, genes, nthr, 25.0)
             line["cpu_baseline"] = {"value": cg / cdt, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample,
                                     "seconds": cdt,
                                     "note": "CPU restatement (oracle/), not CmdStan: CmdStan cannot be built in this image"}

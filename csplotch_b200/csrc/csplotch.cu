@@ -20,6 +20,7 @@
 
 #include "../../include/csplotch.h"
 #include "device_ops.cuh"
+#include "warp_ops.cuh"
 
 using namespace csp;
 
@@ -80,6 +81,9 @@ struct csplotch_model {
   std::vector<ClusterVariant> clv;
   int max_cl = 1;        // the largest cluster size worth using on this design (by its tile count)
   int forced_cl = 0;     // CSPLOTCH_CLUSTER at model creation (tests / A-B measurements): always use this size
+  bool warp_ok = false;  // small design: a gene-chain can run on one warp (warp_ops.cuh)
+  int forced_scope = -1; // CSPLOTCH_SCOPE=cta|warp at model creation: 0 / 1, -1 = by the number of gene-chains
+  size_t warp_smem_bytes = 0;
 };
 
 // the model descriptor of a launch with clusters of `cl` CTAs (cl == 1: the plain one)
@@ -141,6 +145,7 @@ struct csplotch_sampler {
   bool timed = false;
   int grid = 0;
   int64_t launches = 0;
+  bool warp_scope = false;           // one gene-chain per warp (small designs, many chains)
   int cl = 1;                        // CTAs per gene-chain of this sampler's launches (choose_cluster)
   DevModel dml;                      // the model descriptor with that cluster partition
   int *order_dev = nullptr;          // [W] queue order of the next launch
@@ -445,6 +450,118 @@ k_nuts_advance(const __grid_constant__ DevModel m_in, const __grid_constant__ Sa
   }
 }
 
+// ---- small designs: one gene-chain per WARP (warp_ops.cuh) --------------------------------------------------------
+constexpr int kWarpCtasPerSm = 3;
+template <int KT>
+__device__ __forceinline__ void bind_warp_smem(WarpOps<KT> &ops, const DevModel &m, double *smem) {
+  const int warp = threadIdx.x >> 5;
+  double *base = smem + (size_t)warp * (2 * m.nbeta + 8);
+  ops.Bw = base;
+  ops.Aw = base + m.nbeta;
+  ops.Sw = base + 2 * m.nbeta;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kBlock, kWarpCtasPerSm)
+k_leapfrog_fixed_w(const __grid_constant__ DevModel m_in, const int *__restrict__ counts, const double *__restrict__ pm,
+                   const double *__restrict__ ps, const double *__restrict__ lgam, const double *__restrict__ nnz, int G,
+                   double *q, double *p, double *g, const double *__restrict__ minv, const int *__restrict__ gene_of, int Bn,
+                   double eps, int n_steps, double *H_out) {
+  __shared__ DevModel s_model;
+  stage_model(s_model, m_in);
+  const DevModel &m = s_model;
+  WarpOps<KT> ops(m);
+  bind_warp_smem(ops, m, smem_d);
+  const int wid = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
+  for (int b = wid; b < Bn; b += nw) {
+    const int gi = gene_of ? gene_of[b] : (b % G);
+    ops.gn.counts = counts + (size_t)gi * m.Nc;
+    ops.gn.pm = pm ? pm + (size_t)gi * m.K : nullptr;
+    ops.gn.ps = ps ? ps + (size_t)gi * m.K : nullptr;
+    ops.gn.lgam = lgam[gi];
+    ops.gn.nnz = nnz[gi];
+    ops.minv = const_cast<double *>(minv) + (size_t)b * m.Di;
+    double *qb = q + (size_t)b * m.Di, *pb = p + (size_t)b * m.Di, *gb = g + (size_t)b * m.Di;
+    double V, K = 0.0;
+    bool fin;
+    ops.template eval<false>(qb, nullptr, nullptr, qb, gb, nullptr, 0.0, &V, nullptr, &fin);
+    for (int s = 0; s < n_steps; ++s) ops.template eval<true>(qb, gb, pb, qb, gb, pb, eps, &V, &K, nullptr);
+    if (n_steps == 0) {
+      double k = 0.0;
+      for (int e = ops.lane; e < m.Di; e += 32) k += ops.minv[e] * pb[e] * pb[e];
+      K = 0.5 * warp_sum(k);
+    }
+    if (ops.lane == 0) H_out[b] = V + K;
+    __syncwarp();
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kBlock, kWarpCtasPerSm)
+k_nuts_advance_w(const __grid_constant__ DevModel m_in, const __grid_constant__ SamplerDev s, int n_iter) {
+  const size_t Di = m_in.Di;
+  long long t_start_ns = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_ns));
+  __shared__ DevModel s_model;
+  stage_model(s_model, m_in);
+  const DevModel &m = s_model;
+  WarpOps<KT> ops(m);
+  bind_warp_smem(ops, m, smem_d);
+  const int slot = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  double *ws = s.ws + (size_t)slot * (size_t)(s.pool_vecs + 6) * Di;
+  for (;;) {
+    int w = 0;
+    if (ops.lane == 0) {
+      const int t = atomicAdd(s.queue, 1);
+      w = t < s.W ? s.order[t] : -1;
+    }
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w < 0) break;
+    const int g = w / s.num_chains, c = w - g * s.num_chains;
+    ops.gn.counts = s.counts + (size_t)g * m.Nc;
+    ops.gn.pm = s.pm ? s.pm + (size_t)g * m.K : nullptr;
+    ops.gn.ps = s.ps ? s.ps + (size_t)g * m.K : nullptr;
+    ops.gn.lgam = s.lgam[g];
+    ops.gn.nnz = s.nnz[g];
+    ops.key = RngKey{s.cfg.seed, (uint32_t)c + 1u, s.gene_ids[g]};
+    ops.pool = ws;
+    ops.zq[0] = ws + (size_t)s.pool_vecs * Di;
+    ops.zg[0] = ops.zq[0] + Di;
+    ops.zq[1] = ops.zg[0] + Di;
+    ops.zg[1] = ops.zq[1] + Di;
+    ops.q_prop = ops.zg[1] + Di;
+    ops.q_samp = ops.q_prop + Di;
+    ops.q_cur = s.q_cur + (size_t)w * Di;
+    ops.minv = s.minv + (size_t)w * Di;
+    ops.wm = s.wm + (size_t)w * Di;
+    ops.wm2 = s.wm2 + (size_t)w * Di;
+    ops.sample_is_q0 = true;
+    const size_t ns = (size_t)s.cfg.num_samples;
+    ops.out_diag = s.diag ? s.diag + (size_t)w * ns * 7 : nullptr;
+    ops.out_small = s.small ? s.small + (size_t)w * ns * m.nsmall_true : nullptr;
+    ops.out_theta = s.theta ? s.theta + (size_t)w * ns * m.D : nullptr;
+    ops.out_summ = s.summ ? s.summ + (size_t)w * 6 * m.N : nullptr;
+    ChainScalars cs = s.cs[w];
+    ops.cyc_eval = ops.cyc_merge = ops.cyc_copy = ops.cyc_other = ops.n_merge = ops.n_copy = ops.cyc_pro = ops.cyc_fin = 0;
+    const long long t_chain = clock64();
+    Nuts<WarpOps<KT>> nuts(ops, s.cfg, cs, ops.key);
+    nuts.advance(n_iter, s.have_init != 0);
+    __syncwarp();
+    if (ops.lane == 0) {
+      cs.cyc_eval += ops.cyc_eval; cs.cyc_merge += ops.cyc_merge; cs.cyc_copy += ops.cyc_copy;
+      cs.n_merge += ops.n_merge; cs.n_copy += ops.n_copy;
+      cs.cyc_other += (clock64() - t_chain) - ops.cyc_eval - ops.cyc_merge - ops.cyc_copy;
+      s.cs[w] = cs;
+    }
+    __syncwarp();
+  }
+  if (ops.lane == 0) {
+    long long t_end_ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end_ns));
+    s.slot_ns[slot] = t_end_ns - t_start_ns;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host: model
 // ------------------------------------------------------------------------------------------------
@@ -702,6 +819,12 @@ extern "C" int32_t csplotch_model_create(const csplotch_shared_desc *d, csplotch
     }
     if (m->forced_cl > 1 && !has_cluster(m, m->forced_cl)) m->forced_cl = m->clv.empty() ? 1 : m->clv.back().cl;
   }
+  m->warp_ok = dm.nbeta <= kWarpMaxBeta && dm.Di <= 32768;
+  m->warp_smem_bytes = (size_t)kWarps * (2 * dm.nbeta + 8) * sizeof(double);
+  if (const char *fs = std::getenv("CSPLOTCH_SCOPE")) {
+    if (std::string(fs) == "warp") m->forced_scope = 1;
+    else if (std::string(fs) == "cta") m->forced_scope = 0;
+  }
   m->smem_bytes = (size_t)(2 * dm.nbeta + kWarps * kRedMax + 10 + kClScratch) * sizeof(double) + (kMaxDesc * sizeof(TmaDesc) + 15) / 16 * 16;
   if (tiled) m->smem_bytes += ((size_t)((dm.look == 1 ? 4 : 8) + 4 * (dm.look + 2)) * kTile + 2) * sizeof(double) + 2 * (size_t)dm.stage_bytes;
   if (!m->clv.empty()) m->smem_bytes += (size_t)2 * dm.look * kTile * sizeof(double);
@@ -954,6 +1077,8 @@ static int sm_count() {
 
 template <class Kern>
 static cudaError_t set_smem(Kern kern, size_t bytes) {
+  // (no cudaFuncAttributePreferredSharedMemoryCarveout: sizing the carve-out by hand for the CTAs the launch bounds
+  //  allow measured 10-13 % SLOWER on c2 / c4 than the driver's own choice, profiles/r02_kernel_experiments.md)
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
@@ -967,6 +1092,19 @@ static int choose_cluster(const csplotch_model *m, long long n_chains) {
   int cl = 1;
   while (cl < m->max_cl && has_cluster(m, 2 * cl) && n_chains * cl < 8 * slots) cl *= 2;
   return cl;
+}
+
+// One warp per gene-chain (warp_ops.cuh) for small designs: selected with CSPLOTCH_SCOPE=warp at model creation.
+static bool choose_warp_scope(const csplotch_model *m, long long n_chains) {
+  if (!m->warp_ok) return false;
+  if (m->forced_scope >= 0) return m->forced_scope == 1;
+  (void)n_chains;
+  return false;   // opt-in (CSPLOTCH_SCOPE=warp): bitwise reproducible, but its un-pipelined spot loop runs c2 at 0.65x the
+                  // CTA path (profiles/r02_kernel_experiments.md); it becomes the default for small designs once that
+                  // loop batches its loads
+}
+static int warp_resident_ctas() {
+  return sm_count() * kWarpCtasPerSm;
 }
 
 // kernels that run one gene-chain per CTA (CLV = false) or per thread-block cluster of CTAs (CLV = true)
@@ -1106,6 +1244,14 @@ extern "C" int32_t csplotch_leapfrog_fixed(csplotch_batch *b, const double *thet
   cudaError_t e = cudaSuccess;
   const int cl = choose_cluster(m, Bn);
   const DevModel dml = with_cluster(m, cl);
+  if (m->warp_ok && m->forced_scope == 1) {
+    DISPATCH_KT(m->kt, {
+      e = set_smem(k_leapfrog_fixed_w<KT>, m->warp_smem_bytes);
+      if (e == cudaSuccess)
+        k_leapfrog_fixed_w<KT><<<std::min((Bn + kWarps - 1) / kWarps, warp_resident_ctas()), kBlock, m->warp_smem_bytes>>>(
+            dm, b->counts, b->pm, b->ps, b->lgam, b->nnz, b->G, q, p, g, mi, go, Bn, eps, n_steps, H);
+    });
+  } else
   DISPATCH_KT_CL(m->kt, cl > 1, {
     e = set_smem(k_leapfrog_fixed<KT, CLV>, m->smem_bytes);
     if (e == cudaSuccess) {
@@ -1166,6 +1312,14 @@ extern "C" int32_t csplotch_leapfrog_bench(csplotch_batch *b, int32_t Bn, double
   const DevModel dml = with_cluster(m, cl);
   for (int r = 0; r <= reps && e == cudaSuccess; ++r) {
     if (r == 1) cudaEventRecord(e0);
+    if (m->warp_ok && m->forced_scope == 1) {
+      DISPATCH_KT(m->kt, {
+        e = set_smem(k_leapfrog_fixed_w<KT>, m->warp_smem_bytes);
+        if (e == cudaSuccess)
+          k_leapfrog_fixed_w<KT><<<std::min((Bn + kWarps - 1) / kWarps, warp_resident_ctas()), kBlock, m->warp_smem_bytes>>>(
+              dm, b->counts, b->pm, b->ps, b->lgam, b->nnz, b->G, q, p, g, mi, (const int *)nullptr, Bn, eps, n_steps, H);
+      });
+    } else
     DISPATCH_KT_CL(m->kt, cl > 1, {
       e = set_smem(k_leapfrog_fixed<KT, CLV>, m->smem_bytes);
       if (e == cudaSuccess) {
@@ -1214,10 +1368,16 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
   sd.cfg = NutsConfig{cfg->num_warmup, cfg->num_samples, cfg->max_depth, cfg->delta, cfg->gamma, cfg->kappa, cfg->t0,
                       cfg->init_buffer, cfg->term_buffer, cfg->window, cfg->init_radius, cfg->stepsize, cfg->seed};
   sd.counts = b->counts; sd.pm = b->pm; sd.ps = b->ps; sd.lgam = b->lgam; sd.nnz = b->nnz;
-  // gene-chains resident at once (CTAs, or clusters of s->cl CTAs)
-  s->cl = choose_cluster(m, W);
+  // gene-chains resident at once (warps, CTAs, or clusters of s->cl CTAs)
+  s->warp_scope = choose_warp_scope(m, W);
+  s->cl = s->warp_scope ? 1 : choose_cluster(m, W);
   s->dml = with_cluster(m, s->cl);
-  {
+  if (s->warp_scope) {
+    cudaError_t e0 = cudaSuccess;
+    DISPATCH_KT(m->kt, { e0 = set_smem(k_nuts_advance_w<KT>, m->warp_smem_bytes); });
+    if (e0 != cudaSuccess) { delete s; return fail(CSPLOTCH_E_CUDA, cudaGetErrorString(e0)); }
+    s->grid = std::min(W, warp_resident_ctas() * kWarps);   // chains; the launch uses ceil(grid / 8) CTAs
+  } else {
     int rc_chains = 0;
     DISPATCH_KT_CL(m->kt, s->cl > 1, {
       cudaError_t e0 = set_smem(k_nuts_advance<KT, CLV>, m->smem_bytes);
@@ -1244,6 +1404,7 @@ extern "C" int32_t csplotch_sampler_create(csplotch_batch *b, const csplotch_nut
     const size_t max_slots = (size_t)(0.9 * (double)(free_b - need)) / per_slot;
     s->grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->grid, max_slots));
   }
+  if (s->warp_scope) s->grid = s->grid >= kWarps ? s->grid / kWarps * kWarps : kWarps;   // whole CTAs of eight chain slots
   sd.n_slots = s->grid;
   cudaError_t e = cudaSuccess;
   auto A = [&](auto **p, size_t n) { if (e == cudaSuccess) e = s->buf.alloc(p, n); };
@@ -1335,6 +1496,13 @@ extern "C" int32_t csplotch_sampler_advance(csplotch_sampler *s, int32_t n_iter,
   CU_TRY(cudaMemsetAsync(s->sd.queue, 0, sizeof(int), s->stream));
   CU_TRY(cudaEventRecord(s->ev0, s->stream));
   cudaError_t e = cudaSuccess;
+  if (s->warp_scope) {
+    DISPATCH_KT(m->kt, {
+      e = set_smem(k_nuts_advance_w<KT>, m->warp_smem_bytes);
+      if (e == cudaSuccess)
+        k_nuts_advance_w<KT><<<s->grid / kWarps, kBlock, m->warp_smem_bytes, s->stream>>>(s->dml, s->sd, n_iter);
+    });
+  } else
   DISPATCH_KT_CL(m->kt, s->cl > 1, {
     e = set_smem(k_nuts_advance<KT, CLV>, m->smem_bytes);
     if (e == cudaSuccess)
@@ -1401,7 +1569,7 @@ extern "C" int32_t csplotch_sampler_profile(csplotch_sampler *s, int64_t *out8) 
 extern "C" int32_t csplotch_sampler_layout(csplotch_sampler *s, int32_t *resident_chains_out, int32_t *cluster_size) {
   if (!s) return fail(CSPLOTCH_E_INVALID, "null argument");
   if (resident_chains_out) *resident_chains_out = s->sd.n_slots;
-  if (cluster_size) *cluster_size = s->cl;
+  if (cluster_size) *cluster_size = s->warp_scope ? 0 : s->cl;   // 0: one gene-chain per warp
   return CSPLOTCH_OK;
 }
 

@@ -1499,6 +1499,89 @@ struct DevOps {
     chain_sum<6>(r);
     return (r[1] > 0 && r[0] > 0) && (r[3] > 0 && r[2] > 0) && (r[5] > 0 && r[4] > 0);
   }
+  // Two merges of a cascade in one pass (nuts_core.h: leaf index with >= 2 trailing ones above level 0): L1 ++ C, then
+  // L2 ++ C' with C' = (L1.pb, C.pe, rho(L1) + rho(C)).  Reads Minv and the nine vectors once and writes only the outer
+  // rho: 11 vector streams where two merge() calls move 16 (C.pe, L1.pb and the inner rho would be re-read, the inner
+  // rho written).  CSPLOTCH_NO_MERGE2 (compile time) restores the one-by-one cascade for A/B runs.
+#ifndef CSPLOTCH_NO_MERGE2
+  static constexpr bool kHasMerge2 = true;
+#else
+  static constexpr bool kHasMerge2 = false;
+#endif
+  __device__ unsigned merge2(SubTree L1, SubTree L2, SubTree C, int rho_out) {
+    const long long t0 = clock64();
+    const unsigned r = merge2_pass(L1, L2, C, rho_out);
+    cyc_merge += clock64() - t0;
+    n_merge += 2;
+    return r;
+  }
+  __device__ __noinline__ unsigned merge2_pass(SubTree L1, SubTree L2, SubTree C, int rho_out) {
+    const double *Apb = vec(L1.pb), *Ape = vec(L1.pe), *Arho = vec(L1.rho);
+    const double *Bpb = vec(L2.pb), *Bpe = vec(L2.pe), *Brho = vec(L2.rho);
+    const double *Cpb = vec(C.pb), *Cpe = vec(C.pe), *Crho = vec(C.rho);
+    double *out = vec(rho_out);
+    double a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0;   // L1 ++ C
+    double d1 = 0, d2 = 0, e1 = 0, e2 = 0, f1 = 0, f2 = 0;   // L2 ++ (L1 ++ C)
+    const double *mv = minv;
+    auto body = [&](const double2 w, const double2 apb, const double2 ape, const double2 arh, const double2 bpb,
+                    const double2 bpe, const double2 brh, const double2 cpb, const double2 cpe, const double2 crh,
+                    double *o) {
+      // inner merge: left = L1, right = C (the same arithmetic as merge_pass)
+      double2 rs;
+      rs.x = arh.x + crh.x;
+      rs.y = arh.y + crh.y;
+      a1 += (w.x * apb.x) * rs.x + (w.y * apb.y) * rs.y;
+      a2 += (w.x * cpe.x) * rs.x + (w.y * cpe.y) * rs.y;
+      const double rbx = arh.x + cpb.x, rby = arh.y + cpb.y;
+      b1 += (w.x * apb.x) * rbx + (w.y * apb.y) * rby;
+      b2 += (w.x * cpb.x) * rbx + (w.y * cpb.y) * rby;
+      const double rcx = crh.x + ape.x, rcy = crh.y + ape.y;
+      c1 += (w.x * ape.x) * rcx + (w.y * ape.y) * rcy;
+      c2 += (w.x * cpe.x) * rcx + (w.y * cpe.y) * rcy;
+      // outer merge: left = L2, right = (pb = L1.pb, pe = C.pe, rho = rs)
+      double2 ro;
+      ro.x = brh.x + rs.x;
+      ro.y = brh.y + rs.y;
+      d1 += (w.x * bpb.x) * ro.x + (w.y * bpb.y) * ro.y;
+      d2 += (w.x * cpe.x) * ro.x + (w.y * cpe.y) * ro.y;
+      const double sbx = brh.x + apb.x, sby = brh.y + apb.y;
+      e1 += (w.x * bpb.x) * sbx + (w.y * bpb.y) * sby;
+      e2 += (w.x * apb.x) * sbx + (w.y * apb.y) * sby;
+      const double scx = rs.x + bpe.x, scy = rs.y + bpe.y;
+      f1 += (w.x * bpe.x) * scx + (w.y * bpe.y) * scy;
+      f2 += (w.x * cpe.x) * scx + (w.y * cpe.y) * scy;
+      *reinterpret_cast<double2 *>(o) = ro;
+    };
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+      const int hi = seg_hi[sgi];
+      int e = seg_lo[sgi] + 2 * threadIdx.x;
+      for (; e + 2 * kBlock < hi; e += 4 * kBlock) {   // two strips: 20 independent 16-byte loads per thread
+        const int f = e + 2 * kBlock;
+        const double2 w0 = CSP_LD2(mv, e), w1 = CSP_LD2(mv, f);
+        const double2 g0 = CSP_LD2(Apb, e), g1 = CSP_LD2(Apb, f);
+        const double2 h0 = CSP_LD2(Ape, e), h1 = CSP_LD2(Ape, f);
+        const double2 i0 = CSP_LD2(Arho, e), i1 = CSP_LD2(Arho, f);
+        const double2 j0 = CSP_LD2(Bpb, e), j1 = CSP_LD2(Bpb, f);
+        const double2 k0 = CSP_LD2(Bpe, e), k1 = CSP_LD2(Bpe, f);
+        const double2 l0 = CSP_LD2(Brho, e), l1 = CSP_LD2(Brho, f);
+        const double2 s0 = CSP_LD2(Cpb, e), s1 = CSP_LD2(Cpb, f);
+        const double2 t0 = CSP_LD2(Cpe, e), t1 = CSP_LD2(Cpe, f);
+        const double2 u0 = CSP_LD2(Crho, e), u1 = CSP_LD2(Crho, f);
+        body(w0, g0, h0, i0, j0, k0, l0, s0, t0, u0, out + e);
+        body(w1, g1, h1, i1, j1, k1, l1, s1, t1, u1, out + f);
+      }
+      for (; e < hi; e += 2 * kBlock)
+        body(CSP_LD2(mv, e), CSP_LD2(Apb, e), CSP_LD2(Ape, e), CSP_LD2(Arho, e), CSP_LD2(Bpb, e), CSP_LD2(Bpe, e),
+             CSP_LD2(Brho, e), CSP_LD2(Cpb, e), CSP_LD2(Cpe, e), CSP_LD2(Crho, e), out + e);
+    }
+    double r[6] = {a1, a2, b1, b2, c1, c2};
+    chain_sum<6>(r);
+    double q[6] = {d1, d2, e1, e2, f1, f2};
+    chain_sum<6>(q);
+    const bool p1 = (r[1] > 0 && r[0] > 0) && (r[3] > 0 && r[2] > 0) && (r[5] > 0 && r[4] > 0);
+    const bool p2 = (q[1] > 0 && q[0] > 0) && (q[3] > 0 && q[2] > 0) && (q[5] > 0 && q[4] > 0);
+    return (p1 ? 1u : 0u) | (p2 ? 2u : 0u);
+  }
   __device__ __noinline__ void copy_vec(double *dst, const double *src) {
     for (int sgi = 0; sgi < nseg; ++sgi) {
       const int hi = seg_hi[sgi];

@@ -84,6 +84,14 @@ struct SubTree {
 //   void   init_uniform(uint32_t attempt, double radius); void set_unit_metric()
 //   void   welford_add(double n); void metric_update(double n)
 //   void   record_draw(const DrawInfo&, int sample_index)
+// Ops may offer `unsigned merge2(SubTree L1, SubTree L2, SubTree C, int rho_out)`: the merges L1 ++ C and then
+// L2 ++ (L1 ++ C) in one pass; bit 0 / bit 1 of the result = the first / second subtree persists, vec(rho_out) = the sum
+// of all three rho (meaningful only when both persist)
+template <class Ops, class = void>
+struct ops_has_merge2 { static constexpr bool value = false; };
+template <class Ops>
+struct ops_has_merge2<Ops, decltype((void)Ops::kHasMerge2)> { static constexpr bool value = Ops::kHasMerge2; };
+
 template <class Ops>
 struct Nuts {
   Ops &ops;
@@ -182,6 +190,18 @@ struct Nuts {
           for (int kk = 0; kk < depth; ++kk)
             if ((lvalid >> kk) & 1u) { refs.add(L[kk].pb); refs.add(L[kk].pe); refs.add(L[kk].rho); }
           const int rho_out = pool_alloc(refs);
+          if constexpr (ops_has_merge2<Ops>::value) {
+            // the next level closes at this leaf too: both merges in ONE pass over the vectors (the inner rho sum and
+            // the momenta the two share never go back to memory: 11 vector streams instead of 16)
+            if ((i >> (k + 1)) & 1) {
+              const unsigned pr = ops.merge2(L[k], L[k + 1], cur, rho_out);
+              cur = SubTree{L[k + 1].pb, cur.pe, rho_out};
+              lvalid &= ~(3u << k);
+              k += 2;
+              if (pr != 3u) { valid = false; break; }
+              continue;
+            }
+          }
           const bool persist = ops.merge(L[k], cur, rho_out);
           cur = SubTree{L[k].pb, cur.pe, rho_out};
           lvalid &= ~(1u << k);

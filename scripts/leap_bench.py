@@ -16,7 +16,7 @@ from csplotch_b200 import api, synth
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    args = [a for a in sys.argv[1:] if a in synth.CONFIGS]
     shapes = args or ["c2", "c3"]
     waves = int(sys.argv[sys.argv.index("--waves") + 1]) if "--waves" in sys.argv else 2
     steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 8

@@ -18,7 +18,10 @@ def probe(name, family, shared, G, nch, iters, chunk):
         done += chunk
         nl = c1["n_grad"] - c0["n_grad"]
         out.append((done, ms, nl, nl / (ms * 1e-3)))
-    print(json.dumps(dict(shape=name, layout=s.layout(), tail=s.launch_tail())), flush=True)
+    try:
+        print(json.dumps(dict(shape=name, layout=s.layout(), tail=s.launch_tail())), flush=True)
+    except AttributeError:
+        pass   # an older library variant (A-B runs)
     pr = s.profile(); tot = sum(pr[k] for k in ("cyc_eval", "cyc_merge", "cyc_copy", "cyc_other"))
     cnt = s.counters()
     print(json.dumps(dict(shape=name, profile={k: round(pr[k] / tot, 3) for k in ("cyc_eval", "cyc_merge", "cyc_copy", "cyc_other")},

@@ -9,6 +9,10 @@
 
 #include "nuts_core.h"
 
+#ifndef EMUL_MERGE2
+#define EMUL_MERGE2 1   // the product default: two merges of a cascade per pass (0: one by one)
+#endif
+
 typedef double (*density_fn)(void *ctx, const double *q, double *grad);
 
 struct HostOps {
@@ -86,6 +90,41 @@ struct HostOps {
     }
     ++merges;
     return (a2 > 0 && a1 > 0) && (b2 > 0 && b1 > 0) && (c2 > 0 && c1 > 0);
+  }
+  // the two-merge cascade step of the device Ops (device_ops.cuh merge2): L1 ++ C, then L2 ++ (L1 ++ C) in one pass
+  static constexpr bool kHasMerge2 = EMUL_MERGE2 != 0;
+  unsigned merge2(csp::SubTree L1, csp::SubTree L2, csp::SubTree C, int rho_out) {
+    const double *Apb = vec(L1.pb), *Ape = vec(L1.pe), *Arho = vec(L1.rho);
+    const double *Bpb = vec(L2.pb), *Bpe = vec(L2.pe), *Brho = vec(L2.rho);
+    const double *Cpb = vec(C.pb), *Cpe = vec(C.pe), *Crho = vec(C.rho);
+    double *out = vec(rho_out);
+    double a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0, d1 = 0, d2 = 0, e1 = 0, e2 = 0, f1 = 0, f2 = 0;
+    for (int i = 0; i < D; ++i) {
+      const double w = minv[i];
+      const double rs = Arho[i] + Crho[i];
+      a1 += (w * Apb[i]) * rs;
+      a2 += (w * Cpe[i]) * rs;
+      const double rb = Arho[i] + Cpb[i];
+      b1 += (w * Apb[i]) * rb;
+      b2 += (w * Cpb[i]) * rb;
+      const double rc = Crho[i] + Ape[i];
+      c1 += (w * Ape[i]) * rc;
+      c2 += (w * Cpe[i]) * rc;
+      const double ro = Brho[i] + rs;
+      d1 += (w * Bpb[i]) * ro;
+      d2 += (w * Cpe[i]) * ro;
+      const double sb = Brho[i] + Apb[i];
+      e1 += (w * Bpb[i]) * sb;
+      e2 += (w * Apb[i]) * sb;
+      const double sc = rs + Bpe[i];
+      f1 += (w * Bpe[i]) * sc;
+      f2 += (w * Cpe[i]) * sc;
+      out[i] = ro;
+    }
+    merges += 2;
+    const bool p1 = (a2 > 0 && a1 > 0) && (b2 > 0 && b1 > 0) && (c2 > 0 && c1 > 0);
+    const bool p2 = (d2 > 0 && d1 > 0) && (e2 > 0 && e1 > 0) && (f2 > 0 && f1 > 0);
+    return (p1 ? 1u : 0u) | (p2 ? 2u : 0u);
   }
   void copy_q_to_prop(int z) { q_prop = zq[z]; ++copies; }
   void swap_prop_sample() { q_prop.swap(q_samp); sample_is_q0 = false; }
