@@ -196,10 +196,13 @@ def ess_leg(api, model, genes, G, n, chains=4, seed=11, ess_genes=64, gene_ids=N
     return out
 
 
-def cpu_reference_run(family, shared, genes, iters, n_threads, n_chains=4):
-    """Bounded CPU sample: n_threads gene-chains (one thread each, like CmdStan's one process per
-    chain) for `iters` warm-up transitions from initialisation; returns (grads, seconds, description).
-    Uses the timing build of the oracle (oracle/Makefile `fast`: -O3 -march=native, rebuilt on this host)."""
+def cpu_reference_run(family, shared, genes, seconds, n_threads, n_chains=4):
+    """Bounded CPU sample: n_threads gene-chains (one thread each, like CmdStan's one process per chain) run Stan's
+    adaptive NUTS from initialisation for `seconds` of wall clock, then stop at their next leapfrog (one max-depth
+    transition of a c3 chain is ~15 s of a host core, so "the first k transitions" cannot be bounded to seconds).
+    Returns (grads, seconds, description, wall seconds): `seconds` is the thread-busy time / threads, i.e.
+    grads / seconds is the rate of a long job whose threads never idle.  Uses the timing build of the oracle
+    (oracle/Makefile `fast`: -O3 -march=native, rebuilt on this host)."""
     if "CSPLOTCH_ORACLE_LIB" not in os.environ:
         import oracle as _o
         os.environ["CSPLOTCH_ORACLE_LIB"] = _o.build_fast()
@@ -208,33 +211,19 @@ def cpu_reference_run(family, shared, genes, iters, n_threads, n_chains=4):
     G = max(1, n_threads // n_chains)
     G = min(G, genes["counts"].shape[0])
     o = oracle.Oracle(synth.gene_dict(shared, genes, 0), family)
-    cfg = oracle.nuts_cfg(iters, 0, seed=1)
+    cfg = oracle.nuts_cfg(1000, 0, seed=1)
     pm = genes["beta_prior_mean"][:G] if "beta_prior_mean" in genes else None
     ps = genes["beta_prior_std"][:G] if "beta_prior_std" in genes else None
     t0 = time.time()
     res = o.nuts_batch(genes["counts"][:G], cfg, n_chains=n_chains, prior_mean=pm, prior_std=ps,
-                       n_threads=n_threads, want_draws=False)
-    dt = time.time() - t0
-    return res["n_grad"], dt, "%d genes x %d chains x first %d NUTS transitions (from initialisation), %d threads, gcc -O3 -march=native" % (
-        G, n_chains, iters, n_threads)
-
-
-def cpu_sample(family, shared, genes, n_threads, target_s):
-    """One bounded CPU sample of about target_s seconds: the first `it` transitions from initialisation, `it` grown
-    while the PREDICTED time of the next, longer run stays inside the budget (trees deepen during early warm-up: a
-    max-depth transition of a c3 chain is ~30 s of one host core, so a prediction from the first two transitions alone
-    under-estimates by 10x).  Returns the last run: (grads, seconds, description, iters)."""
-    it = 2
-    g, dt, sample = cpu_reference_run(family, shared, genes, it, n_threads)
-    spent = dt
-    while it < 400:
-        nxt = min(400, max(it + 1, int(it * 1.5)))
-        if 2.0 * dt * nxt / it > target_s - spent:      # (2x: the later transitions are the deeper ones)
-            break
-        it = nxt
-        g, dt, sample = cpu_reference_run(family, shared, genes, it, n_threads)
-        spent += dt
-    return g, dt, sample, it
+                       n_threads=n_threads, want_draws=False, time_budget=seconds)
+    wall = time.time() - t0
+    workers = min(n_threads, G * n_chains)
+    busy = res.get("busy_seconds", 0.0) / max(1, workers)
+    dt = busy if busy > 0 else wall
+    return res["n_grad"], dt, ("%d genes x %d chains, adaptive NUTS (max_depth 10) from initialisation for %.1f s of wall clock, "
+                               "%d threads, gcc -O3 -march=native; rate = gradients / (thread-busy seconds / threads)"
+                               % (G, n_chains, seconds, n_threads)), wall
 
 
 def run_reference(args):
@@ -248,21 +237,23 @@ def run_reference(args):
     # the same genes as the cpu_baseline leg of the GPU arm: the head of the workload's gene list
     family, shared, genes = make_inputs(wl_name, WORKLOADS[wl_name][1], 0, head_only=True)
     nthr = os.cpu_count() or 1
-    # every step is one bounded sample; the whole arm (warm-up + steps) aims at <= ~3 minutes of host time
-    iters = args.cpu_iters or cpu_sample(family, shared, genes, nthr, 150.0 / max(1, args.steps + args.warmup))[3]
+    # every step is one time-bounded sample; the whole arm (warm-up + steps) takes ~2.5 minutes of host time
+    n_runs = max(1, args.steps + args.warmup)
+    iters = float(args.cpu_iters) if args.cpu_iters else max(2.0, 150.0 / n_runs)
     for _ in range(args.warmup):
         cpu_reference_run(family, shared, genes, iters, nthr)
-    tot_g, tot_t, sample = 0, 0.0, ""
+    tot_g, tot_t, tot_wall, sample = 0, 0.0, 0.0, ""
     for _ in range(args.steps):
-        g, dt, sample = cpu_reference_run(family, shared, genes, iters, nthr)
-        tot_g += g; tot_t += dt
+        g, dt, sample, wall = cpu_reference_run(family, shared, genes, iters, nthr)
+        tot_g += g; tot_t += dt; tot_wall += wall
     val = tot_g / tot_t
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_wall / max(1, args.steps), "higher_is_better": True,
         "scaling": "strong" if wl_name in STRONG else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[wl_name][3]},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port", "sample": "per step: " + sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port", "sample": "per step: " + sample,
+                         "wall_clock_value": tot_g / tot_wall},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "CPU restatement of the Stan models + Stan NUTS (oracle/), not CmdStan: CmdStan cannot be built here",
@@ -301,7 +292,7 @@ def main():
     ap.add_argument("--genes", type=int, default=0, help="genes in the list (c3/c5) or per GPU (c2/c4)")
     ap.add_argument("--iters", type=int, default=0, help="NUTS transitions per chain per step")
     ap.add_argument("--chains", type=int, default=4)
-    ap.add_argument("--cpu-iters", type=int, default=0)
+    ap.add_argument("--cpu-iters", type=int, default=0, help="seconds of wall clock of one CPU sample (default: 20, or 150 / (steps + warmup) per step of --impl reference)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-genes", type=int, default=0)
     ap.add_argument("--e2e-iters", type=int, default=0, help="NUTS transitions per chain in one e2e step")
@@ -542,12 +533,9 @@ def main():
             line["secondary"] = secondary
         if world == 1 and not args.no_cpu:
             nthr = os.cpu_count() or 1
-            if args.cpu_iters:
-                cg, cdt, sample = cpu_reference_run(family, shared, genes, args.cpu_iters, nthr)
-            else:
-                cg, cdt, sample, _ = cpu_sample(family, shared, genes, nthr, 25.0)
+            cg, cdt, sample, cwall = cpu_reference_run(family, shared, genes, float(args.cpu_iters or 20), nthr)
             line["cpu_baseline"] = {"value": cg / cdt, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample,
-                                    "seconds": cdt,
+                                    "seconds": cwall, "wall_clock_value": cg / cwall,
                                     "note": "CPU restatement (oracle/), not CmdStan: CmdStan cannot be built in this image"}
         emit(line)
     if world > 1:

@@ -238,10 +238,17 @@ __global__ void k_summ_finalize(const double *__restrict__ summ, const ChainScal
 // ------------------------------------------------------------------------------------------------
 // main kernels
 // ------------------------------------------------------------------------------------------------
-// resident CTAs per SM: the non-compositional models (KT <= 2) need few enough registers for three
+// resident CTAs per SM: two, at 128 registers per thread, for every kernel.  Round 1 ran the non-compositional models
+// (KT <= 2) at three CTAs of 80 registers; with this round's tile loop that build spills inside it (555 LDL / 476 STL in
+// the K = 1 leapfrog, and how many end up in the hot loop changed from build to build), and two CTAs of 128 registers
+// measured +8 % on the c2 leapfrog, +4 % on the c2 sampler and +49 % on the c4 leapfrog (LOOK = 2, 283 MB of workspace
+// per resident CTA) — GPU call 17, profiles/r02_kernel_experiments.md.  CSP_SMALL_CTAS=3 rebuilds the old setting.
+#ifndef CSP_SMALL_CTAS
+#define CSP_SMALL_CTAS 2
+#endif
 template <int KT>
-constexpr int kCtasPerSm = KT <= 2 ? 3 : 2;
-static int ctas_per_sm(int kt) { return kt <= 2 ? 3 : 2; }
+constexpr int kCtasPerSm = KT <= 2 ? CSP_SMALL_CTAS : 2;
+static int ctas_per_sm(int kt) { return kt <= 2 ? CSP_SMALL_CTAS : 2; }
 __device__ __forceinline__ void stage_model(DevModel &dst, const DevModel &src) {
   const int n = (int)(sizeof(DevModel) / sizeof(int));
   for (int i = threadIdx.x; i < n; i += blockDim.x) reinterpret_cast<int *>(&dst)[i] = reinterpret_cast<const int *>(&src)[i];

@@ -106,6 +106,7 @@ def lib():
         _lib = C.CDLL(alt or _LIB_PATH)
         _lib.orc_log_prob_grad.restype = C.c_double
         _lib.orc_nuts_batch.restype = C.c_int64
+        _lib.orc_last_batch_busy_seconds.restype = C.c_double
         _lib.orc_dim.restype = C.c_int32
         _lib.orc_num_spots.restype = C.c_int32
         _lib.orc_num_outputs.restype = C.c_int32
@@ -228,18 +229,23 @@ class Oracle:
 
     # -- gene-parallel batches (CPU baseline) -------------------------------
     def nuts_batch(self, counts, cfg, n_chains=4, prior_mean=None, prior_std=None, gene_id0=0,
-                   n_threads=0, want_draws=True):
+                   n_threads=0, want_draws=True, time_budget=0.0):
+        """time_budget > 0 (bench.py's bounded CPU samples): every chain stops at its next leapfrog once that many
+        seconds have passed; n_grad counts what was done."""
         counts = np.ascontiguousarray(counts, dtype=np.int32).reshape(-1, self.N)
         G = counts.shape[0]
         pm = _f64(prior_mean) if prior_mean is not None else None
         ps = _f64(prior_std) if prior_std is not None else None
         draws = np.zeros((G, n_chains, cfg.num_samples, 7 + self.dim)) if want_draws else None
         status = np.zeros(G * n_chains, dtype=np.int32)
+        lib().orc_set_time_budget(C.c_double(time_budget))
         ng = lib().orc_nuts_batch(C.byref(self.c), _ptr(counts), _ptr(pm) if pm is not None else None,
                                   _ptr(ps) if ps is not None else None, C.c_int32(G), C.c_int32(n_chains),
                                   C.byref(cfg), C.c_uint32(gene_id0), C.c_int32(n_threads),
                                   _ptr(draws) if want_draws else None, _ptr(status))
-        return dict(draws=draws, status=status.reshape(G, n_chains), n_grad=int(ng))
+        lib().orc_set_time_budget(C.c_double(0.0))
+        return dict(draws=draws, status=status.reshape(G, n_chains), n_grad=int(ng),
+                    busy_seconds=float(lib().orc_last_batch_busy_seconds()))
 
     def log_prob_grad_batch(self, counts, theta, gene_of=None, prior_mean=None, prior_std=None,
                             jacobian=True, n_threads=0):

@@ -606,7 +606,28 @@ typedef struct {
   int64_t n_grad;
   double *tmp;
   ps_t z;
+  int aborted;   /* the time budget of orc_set_time_budget ran out inside a trajectory */
 } hmc_t;
+
+/* bench.py's CPU legs time a BOUNDED sample: with a budget set, every chain of the process stops at its next leapfrog
+ * once the deadline has passed (one max-depth transition of a c3 chain is ~15 s of a host core, so "the first k
+ * transitions" cannot be bounded to a few seconds).  0 = no budget (the default: parity runs are never cut). */
+static double g_deadline = 0.0;
+void orc_set_time_budget(double seconds) {
+#ifdef _OPENMP
+  g_deadline = seconds > 0 ? omp_get_wtime() + seconds : 0.0;
+#else
+  (void)seconds;
+  g_deadline = 0.0;
+#endif
+}
+static int past_deadline(void) {
+#ifdef _OPENMP
+  return g_deadline > 0.0 && omp_get_wtime() > g_deadline;
+#else
+  return 0;
+#endif
+}
 
 static void ps_alloc(ps_t *z, int D) {
   z->q = (double *)calloc((size_t)D, sizeof(double));
@@ -696,6 +717,7 @@ static int build_tree(hmc_t *s, int depth, double *p_sharp_beg, double *p_sharp_
     double h, w, u;
     leapfrog(s, &s->z, sign * s->eps);
     tr->n_leapfrog++;
+    if (past_deadline()) { s->aborted = 1; return 0; }
     h = hamil(s, &s->z);
     if (isnan(h)) h = INFINITY;
     if ((h - tr->H0) > s->max_deltaH) tr->divergent = 1;
@@ -1024,6 +1046,7 @@ int32_t orc_nuts_generic(orc_density_fn fn, void *ctx, int32_t D, const orc_nuts
     int warm = it < cfg->num_warmup;
     if (it == cfg->num_warmup) s.eps = exp(da.x_bar); /* complete_adaptation */
     nuts_transition(&s, q, (uint32_t)it, &info);
+    if (s.aborted) break;
     if (warm) {
       int update;
       da_learn(&da, &s.eps, info.accept_stat);
@@ -1096,10 +1119,17 @@ void orc_leapfrog_fixed(const orc_data *d, const double *theta0, const double *p
 /* ------------------------------------------------------------------ */
 /* gene-parallel batches (CPU baseline; one thread per gene-chain)     */
 /* ------------------------------------------------------------------ */
+/* seconds the worker threads of the last orc_nuts_batch call spent inside chains, summed over threads: the bounded
+ * samples bench.py times are a handful of chains of very different lengths, so their wall clock is the longest chain's;
+ * gradients / (busy seconds / threads) is the rate of the long, balanced job such a sample stands for */
+static double g_busy_seconds = 0.0;
+double orc_last_batch_busy_seconds(void) { return g_busy_seconds; }
+
 int64_t orc_nuts_batch(const orc_data *shared, const int32_t *counts, const double *prior_mean,
                        const double *prior_std, int32_t G, int32_t n_chains, const orc_nuts_cfg *cfg,
                        uint32_t gene_id0, int32_t n_threads, double *draws, int32_t *status) {
   int64_t total = 0;
+  double busy = 0.0;
   int N = orc_num_spots(shared), D = orc_dim(shared), K = shared->family == 1 ? shared->N_celltypes : 1;
   int w;
   (void)n_threads;
@@ -1111,13 +1141,16 @@ int64_t orc_nuts_batch(const orc_data *shared, const int32_t *counts, const doub
 #endif
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
-#pragma omp parallel for schedule(dynamic) reduction(+ : total)
+#pragma omp parallel for schedule(dynamic) reduction(+ : total, busy)
 #endif
   for (w = 0; w < G * n_chains; ++w) {
     int g = w / n_chains, c = w % n_chains;
     orc_data d = *shared;
     int64_t ng = 0;
     int32_t st;
+#ifdef _OPENMP
+    const double t_item = omp_get_wtime();
+#endif
     double *out = draws ? draws + ((size_t)w * (size_t)cfg->num_samples) * (size_t)(7 + D) : NULL;
     d.counts = counts + (size_t)g * (size_t)N;
     if (prior_mean) d.beta_prior_mean = prior_mean + (size_t)g * (size_t)K;
@@ -1125,7 +1158,11 @@ int64_t orc_nuts_batch(const orc_data *shared, const int32_t *counts, const doub
     st = orc_nuts_run(&d, cfg, gene_id0 + (uint32_t)g, (uint32_t)c + 1u, NULL, 0, out, NULL, NULL, &ng);
     if (status) status[w] = st;
     total += ng;
+#ifdef _OPENMP
+    busy += omp_get_wtime() - t_item;
+#endif
   }
+  g_busy_seconds = busy;
 #ifdef ORC_FAST
   g_lsf = NULL;
   g_lsf_src = NULL;

@@ -122,6 +122,13 @@ int64_t orc_nuts_batch(const orc_data *shared, const int32_t *counts, const doub
                        const double *prior_std, int32_t G, int32_t n_chains, const orc_nuts_cfg *cfg,
                        uint32_t gene_id0, int32_t n_threads, double *draws, int32_t *status);
 
+/* wall-clock budget for the chains of this process from now on (bench.py's bounded CPU samples): once it has run out
+ * every chain stops at its next leapfrog; seconds <= 0 removes the budget (default) */
+void orc_set_time_budget(double seconds);
+
+/* thread-busy seconds of the last orc_nuts_batch call, summed over its worker threads (0 without OpenMP) */
+double orc_last_batch_busy_seconds(void);
+
 /* batch of stand-alone gradient evaluations (CPU baseline for the lp+grad kernel) */
 void orc_log_prob_grad_batch(const orc_data *shared, const int32_t *counts, const double *prior_mean,
                              const double *prior_std, int32_t G, const double *theta, int32_t B,

@@ -30,7 +30,7 @@ def main():
         genes = synth.simulate_counts(shared, 16, 5)
         model = api.Model(shared, cfg["family"])
         batch = api.Batch(model, genes["counts"], genes.get("beta_prior_mean"), genes.get("beta_prior_std"))
-        per_sm = 3 if model.K <= 2 else 2
+        per_sm = 2                      # resident CTAs per SM of every kernel (round 1: 3 for K <= 2)
         per_sm = int(os.environ.get("CSP_CTAS_PER_SM", per_sm))
         for w in sorted({1, waves}):
             B = 148 * per_sm * w

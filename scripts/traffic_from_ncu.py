@@ -5,7 +5,7 @@ import csv, json, sys
 
 tag, shape = sys.argv[1], sys.argv[2]
 idx = int(sys.argv[3]) if len(sys.argv) > 3 else 1        # index into the launches list of the launch ncu profiled (NCU_SKIP)
-rows = list(csv.reader(open("gpurun_out/raw_%s.csv" % tag)))
+rows = [r for r in csv.reader(l for l in open("gpurun_out/raw_%s.csv" % tag) if not l.startswith("==")) if r]
 hdr, unit, val = rows[0], rows[1], rows[2]
 
 
@@ -23,8 +23,8 @@ N, D = info["N"], info["D"]
 rd, wr = metric("dram__bytes_read.sum"), metric("dram__bytes_write.sum")
 alg = (L["leapfrogs"] * (56 * D + 4 * N) + (L["grads"] - L["leapfrogs"]) * (16 * D + 4 * N)) / L["grads"]
 out = {
-    "source": "ncu --set full --clock-control none, k_nuts_advance, scripts/profile_nuts.py %s %d (launch %d: %d gradient "
-              "evaluations, %d leapfrogs)" % (shape, info["G"], idx, L["grads"], L["leapfrogs"]),
+    "source": "ncu --clock-control none (dram__bytes_read/write.sum), k_nuts_advance, one gene-chain per CTA, "
+              "scripts/profile_nuts.py %s %d (launch %d: %d gradient evaluations, %d leapfrogs)" % (shape, info["G"], idx, L["grads"], L["leapfrogs"]),
     "dram_bytes_read": rd, "dram_bytes_write": wr, "grad_evals": L["grads"], "leapfrogs": L["leapfrogs"],
     "dram_bytes_per_grad": (rd + wr) / L["grads"], "algorithmic_bytes_per_grad": alg,
     "duration_s_under_ncu": metric("gpu__time_duration.sum"),
