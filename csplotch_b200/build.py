@@ -18,7 +18,10 @@ NVCC_FLAGS = [
     "-ccbin", "/usr/bin/g++",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "--split-compile", "0",     # the kernels of this one translation unit are optimised on all host cores
+    # NO --split-compile: with `--split-compile 0` (optimise on all host cores, 2x faster to build) the output for this
+    # translation unit is NOT deterministic — three sequential builds of one source gave 944 / 944 / 912-byte frames for
+    # k_leapfrog_fixed<10>, and the 944-byte variant runs the c3 leapfrog at 0.27 of the HBM roof against 0.40
+    # (profiles/r02_kernel_experiments.md, GPU call 20).  The single-threaded default is reproducible and the fastest.
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
