@@ -46,3 +46,11 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "csplotch_oracle" not in txt, f
+
+
+def test_build_is_single_threaded_and_targets_sm_100a():
+    """`nvcc --split-compile 0` produced two code variants of the tile loop from one source, a third apart in speed
+    (profiles/r02_kernel_experiments.md): the product build must stay reproducible."""
+    from csplotch_b200 import build as b
+    assert not any("split-compile" in f for f in b.NVCC_FLAGS)
+    assert "arch=compute_100a,code=sm_100a" in b.NVCC_FLAGS and "-lineinfo" in b.NVCC_FLAGS

@@ -108,3 +108,38 @@ def test_random_gaussians_windows_and_depths(D, log_sd, nw, seed, max_depth, del
     # search, reused by every attempt — while the oracle, like upstream, re-evaluates it per attempt; so the oracle's
     # count can only be the larger one (the rate the product reports is not inflated)
     assert 0 <= ng.value - got["n_grad"] <= 8 + ng.value // 5
+
+
+def test_two_merges_per_pass_equal_one_by_one_bit_for_bit():
+    """The merge2 cascade step (nuts_core.h: a leaf that closes two levels above level 0 runs both U-turn merges in one
+    pass, the inner rho sum never stored) makes the same decisions and leaves the same vectors as two single merges:
+    identical draws, to the last bit, on targets whose trees reach depth 6-10."""
+    D = 9
+    sd = np.geomspace(0.05, 6.0, D)
+    arr, ctx = _gauss_ctx(sd)
+    fn = C.cast(oracle.lib().orc_gauss_density, C.c_void_p)
+    for seed in (1, 2, 3):
+        cfg = oracle.nuts_cfg(60, 40, seed=seed)
+        a = emul.nuts_run(fn, ctx, D, cfg, gene_id=5, chain_id=1, chunk=11, merge2=True)
+        b = emul.nuts_run(fn, ctx, D, cfg, gene_id=5, chain_id=1, chunk=11, merge2=False)
+        assert a["status"] == 0 and b["status"] == 0
+        assert a["draws"][:, 3].max() >= 3          # deep enough for a two-level cascade
+        assert np.array_equal(a["draws"], b["draws"])
+        assert a["n_leapfrog"] == b["n_leapfrog"] and a["stepsize"] == b["stepsize"]
+
+
+def test_time_budget_bounds_a_cpu_sample():
+    """bench.py's CPU legs: with a wall-clock budget every chain of orc_nuts_batch stops at its next leapfrog once the
+    budget is spent (gradients done so far are counted), and the budget is cleared afterwards."""
+    import time
+    shared = synth.shared_tiny(seed=5, family="comp_splotch_stan_model", n_levels=3, zi=1, car=1)
+    genes = synth.simulate_counts(shared, 2, 8)
+    o = oracle.Oracle(synth.gene_dict(shared, genes, 0), "comp_splotch_stan_model")
+    t0 = time.time()
+    res = o.nuts_batch(genes["counts"], oracle.nuts_cfg(100000, 0, seed=1), n_chains=2, prior_mean=genes["beta_prior_mean"],
+                       prior_std=genes["beta_prior_std"], n_threads=4, want_draws=False, time_budget=0.5)
+    dt = time.time() - t0
+    assert 0.4 < dt < 5.0 and res["n_grad"] > 100 and res["busy_seconds"] > 0
+    full = o.nuts_batch(genes["counts"], oracle.nuts_cfg(5, 3, seed=1), n_chains=2, prior_mean=genes["beta_prior_mean"],
+                        prior_std=genes["beta_prior_std"], n_threads=4)
+    assert (full["status"] == 0).all() and full["draws"].shape[2] == 3 and np.isfinite(full["draws"]).all()
