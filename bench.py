@@ -355,6 +355,19 @@ def main():
     del genes_all
     note("synthetic inputs ready (%d genes in the list, %d on this rank)" % (G_list if strong else G_list * world, G))
     model = api.Model(shared, family)
+    # The resident arm runs one gene-chain per plain CTA whatever the number of chains.  Left to itself the library puts
+    # launches of few chains (a strong-scaling share at N = 8: 296) on 4-CTA clusters, which is right for jobs run from
+    # initialisation (the e2e and ESS legs below: 104 k against 87 k grad/s, GPU call 24) but not for a launch that
+    # advances every chain by ONE transition of comparable depth (141 k against 105 k): the cluster's shorter latency buys
+    # nothing there and its serial rank-0 epilogue costs 28 % of the throughput.  CSPLOTCH_CLUSTER is the library's
+    # documented knob (read at model creation); a value set by the caller wins.
+    model_res = model
+    if "CSPLOTCH_CLUSTER" not in os.environ:
+        os.environ["CSPLOTCH_CLUSTER"] = "1"
+        try:
+            model_res = api.Model(shared, family)
+        finally:
+            del os.environ["CSPLOTCH_CLUSTER"]
     N, D = model.N, model.dim
     B_leap, B_grad = 56 * D + 4 * N, 16 * D + 4 * N
 
@@ -387,7 +400,9 @@ def main():
                     launches=c1["n_launches"] - c0["n_launches"], clocks=clk, tail=float(np.mean(tails)), profile=prof,
                     total_iters=total_iters)
 
-    r = resident(model, genes, gene_ids, iters, args.steps, args.warmup, ClockSampler(local) if rank == 0 else None)
+    r = resident(model_res, genes, gene_ids, iters, args.steps, args.warmup, ClockSampler(local) if rank == 0 else None)
+    if model_res is not model:
+        model_res.close()
     ms_dev, grads, leaps, launches, clk, t_wall = r["ms"], r["grads"], r["leaps"], r["launches"], r["clocks"], r["wall"]
     note("resident arm: %d timed steps done (launch tail %.1f %%)" % (args.steps, 100 * r["tail"]))
 
@@ -504,6 +519,7 @@ def main():
             "config": {"workload": wl[3], "genes_in_list": G_list if strong else G_list * world,
                        "genes_on_rank0": G, "chains": args.chains,
                        "nuts_transitions_per_chain_per_step": iters,
+                       "resident_scope": "one gene-chain per CTA (CSPLOTCH_CLUSTER=1 for the resident arm; e2e and ess legs: the library's own choice)",
                        "sharding": ("one fixed gene list for every N, dealt longest-first over the ranks (shard.deal), "
                                     "no data-path collective") if strong else "a slice of the gene list per GPU",
                        "l2_policy": "inputs larger than L2: %.1f GB of chain state per GPU streamed every step"
