@@ -538,6 +538,9 @@ def main():
                          "fp64_flops_per_leapfrog": N * (150.0 + 4.0 * K), "fp64_peak_tflops_measured": fpk,
                          "fp64_frac": (flops / (ms_dev * 1e-3) / 1e12 / fpk) if fpk else None,
                          "launch_tail_frac": tail,
+                         # the same fraction over the time the resident slots were busy (a production launch advances
+                         # chains by tens of transitions and has no such tail): achieved / (1 - tail) / peak
+                         "frac_excluding_launch_tail": (achieved / peak / (1.0 - tail)) if tail < 1.0 else None,
                          "time_shares": {k[4:]: prof[k] / ptot for k in ("cyc_eval", "cyc_merge", "cyc_copy", "cyc_other")}},
             "clocks": clk,
             "leapfrogs": leaps, "grad_evals": grads, "wall_s": t_wall,
