@@ -1084,8 +1084,9 @@ static int sm_count() {
 
 template <class Kern>
 static cudaError_t set_smem(Kern kern, size_t bytes) {
-  // (no cudaFuncAttributePreferredSharedMemoryCarveout: sizing the carve-out by hand for the CTAs the launch bounds
-  //  allow measured 10-13 % SLOWER on c2 / c4 than the driver's own choice, profiles/r02_kernel_experiments.md)
+  // (no cudaFuncAttributePreferredSharedMemoryCarveout: the driver's own choice keeps two CTAs resident up to 112 kB each
+  //  (tools/occ_probe.cu); a hand-sized carve-out was no faster in the one run that tried it, and that run is not
+  //  conclusive — profiles/r02_kernel_experiments.md, "build non-determinism")
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
